@@ -1,0 +1,139 @@
+/* groth16-cuda: C ABI of the B200-native MSM engine (libg16cuda.so).
+ *
+ * This is the drop-in boundary for the Groth16 prover/setup of vats98754/zero-knowledge-proofs.
+ * The reference has no FFI today; these entry points are what a `groth16-cuda` Rust crate binds
+ * (see INTEGRATION.md and zero-knowledge-proofs_b200/rust/groth16-cuda) to replace:
+ *
+ *   g16_g1_msm / g16_g1_msm_oneshot   ark `G1Projective::msm(&points,&scalars)` + `.into_affine()`
+ *                                     crates/groth16-core/src/lib.rs:282,285 (Prover::multi_scalar_mult_g1, :275-286)
+ *   g16_g2_msm / g16_g2_msm_oneshot   `G2Projective::msm` + `.into_affine()`          lib.rs:296,299 (:289-300)
+ *   g16_g1_fixed_base_mul             `(g1_gen * fr).into_affine()` per element        crates/groth16-setup/src/lib.rs:166-171,185-191,194-199,210-218,221-229,232-241
+ *   g16_g2_fixed_base_mul             `(g2_gen * fr).into_affine()` per element        crates/groth16-setup/src/lib.rs:168-171,201-207
+ *   g16_pk_upload / g16_prove         the 4 x G1 + 1 x G2 MSM schedule of Prover::prove crates/groth16-core/src/lib.rs:164-271
+ *
+ * Data layout = ark-ff 0.4 / ark-ec 0.4 in-memory values, no conversion on the host:
+ *   Fr scalar : 4 x u64 little-endian limbs, Montgomery form (a * 2^256 mod r)
+ *   Fq        : 6 x u64 little-endian limbs, Montgomery form (a * 2^384 mod q)
+ *   G1 affine : 12 x u64 = x[6], y[6];  infinity flag in a separate byte array (ark's identity is
+ *               {x:0, y:0, infinity:true}; outputs follow that convention)
+ *   G2 affine : 24 x u64 = x.c0[6], x.c1[6], y.c0[6], y.c1[6]; flag as above
+ *   Proof     : a (G1), b (G2), c (G1) in that order, as in `struct Proof` lib.rs:27-36
+ *
+ * All functions return 0 on success and a non-zero G16_ERR_* code otherwise; the message is
+ * available from g16_last_error().  There is no CPU fallback: without a CUDA device every
+ * compute entry point fails with G16_ERR_NO_DEVICE.  A ctx may be used by one thread at a time.
+ * Caller owns all input/output buffers; handles are owned by the library until *_free/_destroy.
+ */
+#ifndef G16_CUDA_H
+#define G16_CUDA_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define G16_OK 0
+#define G16_ERR_INVALID 1   /* bad argument (NULL pointer, wrong group, ...) */
+#define G16_ERR_CUDA 2      /* CUDA runtime error */
+#define G16_ERR_NO_DEVICE 3 /* no usable CUDA device */
+#define G16_ERR_OOM 4       /* device allocation failed */
+#define G16_ERR_LENGTH 5    /* bases / scalars length mismatch (ark: Err(min_len), lib.rs:283,297) */
+
+typedef struct g16_ctx g16_ctx;
+typedef struct g16_bases g16_bases; /* device-resident base points of one group, sharded over the ctx devices */
+typedef struct g16_pk g16_pk;       /* device-resident ProvingKey arrays (crates/groth16-setup/src/lib.rs:27-52) */
+
+/* ---- context ------------------------------------------------------------------------- */
+/* devices == NULL or ndev == 0: use the current CUDA device.  With ndev > 1 every bases
+ * array is partitioned by index range over the devices and each MSM ends with a partial-sum
+ * combine on devices[0]. */
+int g16_ctx_create(const int *devices, int ndev, g16_ctx **out);
+void g16_ctx_destroy(g16_ctx *ctx);
+const char *g16_last_error(const g16_ctx *ctx); /* ctx may be NULL: last error of ctx creation */
+/* run single-device work on the caller's cudaStream_t (e.g. torch's current stream) */
+int g16_ctx_set_stream(g16_ctx *ctx, void *cuda_stream);
+int g16_ctx_synchronize(g16_ctx *ctx);
+/* tuning: window bits for the next MSMs (0 = choose from n) */
+int g16_ctx_set_window_bits(g16_ctx *ctx, unsigned c);
+int g16_device_count(void);
+const char *g16_version(void);
+
+/* ---- variable-base MSM --------------------------------------------------------------- */
+int g16_g1_bases_upload(g16_ctx *ctx, const uint64_t *xy, const uint8_t *inf, size_t n, g16_bases **out);
+int g16_g2_bases_upload(g16_ctx *ctx, const uint64_t *xy, const uint8_t *inf, size_t n, g16_bases **out);
+/* wrap points that already live on the ctx's (single) device in the packed layout above with
+ * (0,0) meaning infinity -- e.g. the output of g16_g1_fixed_base_mul_device.  Not owned. */
+int g16_g1_bases_from_device(g16_ctx *ctx, const void *dev_xy, size_t n, g16_bases **out);
+int g16_g2_bases_from_device(g16_ctx *ctx, const void *dev_xy, size_t n, g16_bases **out);
+void g16_bases_free(g16_bases *bases);
+size_t g16_bases_len(const g16_bases *bases);
+
+/* sum_i scalars[i] * bases[i] for i < n (n <= len(bases)); host scalars, host result */
+int g16_g1_msm(g16_ctx *ctx, const g16_bases *bases, const uint64_t *scalars, size_t n, uint64_t out_xy[12],
+               uint8_t *out_inf);
+int g16_g2_msm(g16_ctx *ctx, const g16_bases *bases, const uint64_t *scalars, size_t n, uint64_t out_xy[24],
+               uint8_t *out_inf);
+/* one call = what Prover::multi_scalar_mult_g1/_g2 does today: fresh bases + scalars from the host */
+int g16_g1_msm_oneshot(g16_ctx *ctx, const uint64_t *xy, const uint8_t *inf, const uint64_t *scalars, size_t n,
+                       uint64_t out_xy[12], uint8_t *out_inf);
+int g16_g2_msm_oneshot(g16_ctx *ctx, const uint64_t *xy, const uint8_t *inf, const uint64_t *scalars, size_t n,
+                       uint64_t out_xy[24], uint8_t *out_inf);
+
+/* Device-resident variants (single-device ctx; asynchronous on the ctx stream).
+ * dev_scalars: n x 4 u64 Montgomery on the device.
+ * dev_out_affine: 12 (G1) / 24 (G2) u64 + one u32 infinity word, may be NULL.
+ * dev_out_partial: projective partial sum, G16_G1_PARTIAL_WORDS / G16_G2_PARTIAL_WORDS u32, may be NULL.
+ * Partials of index-range shards computed by different processes/GPUs are exchanged by the caller
+ * (NCCL all-gather of raw bytes) and folded with g16_*_combine_partials_device. */
+#define G16_G1_PARTIAL_WORDS 48
+#define G16_G2_PARTIAL_WORDS 96
+#define G16_G1_AFFINE_WORDS 25
+#define G16_G2_AFFINE_WORDS 49
+int g16_g1_msm_device(g16_ctx *ctx, const g16_bases *bases, const void *dev_scalars, size_t n, void *dev_out_affine,
+                      void *dev_out_partial);
+int g16_g2_msm_device(g16_ctx *ctx, const g16_bases *bases, const void *dev_scalars, size_t n, void *dev_out_affine,
+                      void *dev_out_partial);
+int g16_g1_combine_partials_device(g16_ctx *ctx, const void *dev_partials, size_t k, void *dev_out_affine);
+int g16_g2_combine_partials_device(g16_ctx *ctx, const void *dev_partials, size_t k, void *dev_out_affine);
+
+/* ---- fixed-base scalar multiplication (CRS generation) --------------------------------- */
+/* out[i] = (base * scalars[i]).into_affine();  out_xy: n x 12 (24) u64, out_inf: n bytes */
+int g16_g1_fixed_base_mul(g16_ctx *ctx, const uint64_t base_xy[12], const uint64_t *scalars, size_t n,
+                          uint64_t *out_xy, uint8_t *out_inf);
+int g16_g2_fixed_base_mul(g16_ctx *ctx, const uint64_t base_xy[24], const uint64_t *scalars, size_t n,
+                          uint64_t *out_xy, uint8_t *out_inf);
+/* device in / device out (packed points, (0,0) = infinity); single-device ctx */
+int g16_g1_fixed_base_mul_device(g16_ctx *ctx, const uint64_t base_xy[12], const void *dev_scalars, size_t n,
+                                 void *dev_out_xy);
+int g16_g2_fixed_base_mul_device(g16_ctx *ctx, const uint64_t base_xy[24], const void *dev_scalars, size_t n,
+                                 void *dev_out_xy);
+
+/* ---- Groth16 prove schedule -------------------------------------------------------------- */
+/* Mirrors `ProvingKey` (crates/groth16-setup/src/lib.rs:27-52): single points as 12/24 u64 with an
+ * infinity byte, vectors as n x 12/24 u64 with optional infinity byte arrays (NULL = none). */
+typedef struct g16_pk_host {
+    const uint64_t *alpha_g1, *beta_g1, *delta_g1; /* 12 u64 each */
+    const uint64_t *beta_g2, *delta_g2;            /* 24 u64 each */
+    const uint64_t *a_g1; const uint8_t *a_g1_inf; size_t a_len;
+    const uint64_t *b_g1; const uint8_t *b_g1_inf; size_t b1_len;
+    const uint64_t *b_g2; const uint8_t *b_g2_inf; size_t b2_len;
+    const uint64_t *ic_g1; const uint8_t *ic_g1_inf; size_t ic_len;
+    const uint64_t *h_g1; const uint8_t *h_g1_inf; size_t h_len;
+    size_t num_public;
+} g16_pk_host;
+int g16_pk_upload(g16_ctx *ctx, const g16_pk_host *pk, g16_pk **out);
+void g16_pk_free(g16_pk *pk);
+/* The group part of Prover::prove (crates/groth16-core/src/lib.rs:164-271).
+ *   assignment_fr : num_vars x 4 u64, the already truncated `assignment_fr` of lib.rs:156-161
+ *   h_coeffs      : h_len_used x 4 u64, `h_coeffs` of lib.rs:203-208 (may be NULL / 0)
+ *   r, s          : 4 u64 each (lib.rs:152-153)
+ * Outputs: proof.a (12 u64 + flag), proof.b (24 u64 + flag), proof.c (12 u64 + flag). */
+int g16_prove(g16_ctx *ctx, const g16_pk *pk, const uint64_t *assignment_fr, size_t num_vars,
+              const uint64_t *h_coeffs, size_t num_h, const uint64_t r[4], const uint64_t s[4],
+              uint64_t a_xy[12], uint8_t *a_inf, uint64_t b_xy[24], uint8_t *b_inf, uint64_t c_xy[12], uint8_t *c_inf);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* G16_CUDA_H */

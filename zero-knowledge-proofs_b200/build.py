@@ -1,0 +1,80 @@
+"""Build libg16cuda.so (sm_100a) in-tree: one nvcc -c per translation unit, in parallel, then link.
+
+    python zero-knowledge-proofs_b200/build.py [--force] [--jobs N] [--verbose]
+
+The library lands in zero-knowledge-proofs_b200/lib/libg16cuda.so (git-ignored; it travels to the
+GPU box with the gpurun snapshot).  Objects are cached under lib/obj and rebuilt when any header or
+the unit itself is newer.
+"""
+from __future__ import annotations
+
+import argparse
+import concurrent.futures as cf
+import glob
+import os
+import subprocess
+import sys
+import time
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIBDIR = os.path.join(HERE, "lib")
+OBJDIR = os.path.join(LIBDIR, "obj")
+LIB = os.path.join(LIBDIR, "libg16cuda.so")
+INCLUDE = os.path.join(os.path.dirname(HERE), "include")
+
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+
+
+def _newest_header() -> float:
+    hdrs = glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(INCLUDE, "*.h"))
+    return max(os.path.getmtime(h) for h in hdrs)
+
+
+def _compile(unit: str, force: bool, verbose: bool):
+    src = os.path.join(CSRC, unit)
+    obj = os.path.join(OBJDIR, unit.replace(".cu", ".o"))
+    log = obj + ".log"
+    if not force and os.path.exists(obj) and os.path.getmtime(obj) >= max(os.path.getmtime(src), _newest_header()):
+        return unit, 0.0, "cached"
+    t0 = time.time()
+    cmd = [NVCC] + ARCH + COMMON + ["-c", src, "-o", obj]
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    with open(log, "w") as f:
+        f.write(res.stdout)
+    if res.returncode != 0:
+        raise RuntimeError(f"nvcc failed for {unit}:\n{res.stdout[-4000:]}")
+    if verbose:
+        print(res.stdout)
+    return unit, time.time() - t0, "built"
+
+
+def build(force: bool = False, jobs: int | None = None, verbose: bool = False) -> str:
+    os.makedirs(OBJDIR, exist_ok=True)
+    units = sorted(os.path.basename(p) for p in glob.glob(os.path.join(CSRC, "*.cu")))
+    jobs = jobs or min(len(units), os.cpu_count() or 4)
+    results = []
+    with cf.ThreadPoolExecutor(max_workers=jobs) as ex:
+        for r in ex.map(lambda u: _compile(u, force, verbose), units):
+            results.append(r)
+    rebuilt = any(r[2] == "built" for r in results)
+    if rebuilt or not os.path.exists(LIB):
+        objs = [os.path.join(OBJDIR, u.replace(".cu", ".o")) for u in units]
+        cmd = [NVCC] + ARCH + ["-shared", "-o", LIB] + objs
+        subprocess.run(cmd, check=True)
+    for unit, dt, what in results:
+        if what == "built":
+            print(f"[build] {unit}: {dt:.1f}s")
+    return LIB
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--force", action="store_true")
+    ap.add_argument("--jobs", type=int, default=None)
+    ap.add_argument("--verbose", action="store_true")
+    a = ap.parse_args()
+    t = time.time()
+    print(build(a.force, a.jobs, a.verbose), f"({time.time() - t:.1f}s)")

@@ -1,0 +1,437 @@
+// C ABI of libg16cuda.so (declared in include/g16_cuda.h).  Also compiled as plain C++ with
+// -DG16_EMU by tests/emu (see rt.cuh) -- that build is test infrastructure only.
+#include "../../include/g16_cuda.h"
+#include "engine.cuh"
+
+using namespace g16;
+
+struct g16_ctx { Context c; };
+struct g16_bases { std::unique_ptr<Bases> b; };
+
+struct g16_pk {
+    Context *ctx = nullptr;
+    // resident arrays with the ad-hoc single points prepended (see g16_prove)
+    std::unique_ptr<Bases> a;    // [alpha_g1, delta_g1, a_g1...]
+    std::unique_ptr<Bases> b2;   // [beta_g2, delta_g2, b_g2...]
+    std::unique_ptr<Bases> b1;   // [beta_g1, b_g1...]
+    std::unique_ptr<Bases> ic;   // ic_g1
+    std::unique_ptr<Bases> h;    // h_g1
+    size_t a_len = 0, b1_len = 0, b2_len = 0, ic_len = 0, h_len = 0, num_public = 0;
+};
+
+static thread_local std::string g_create_error;
+
+template <class Fn>
+static int guarded(g16_ctx *ctx, Fn &&fn) {
+    try {
+        fn();
+        return G16_OK;
+    } catch (const Error &e) {
+        if (ctx) ctx->c.err = e.msg; else g_create_error = e.msg;
+        return e.code;
+    } catch (const std::bad_alloc &) {
+        if (ctx) ctx->c.err = "host allocation failed"; else g_create_error = "host allocation failed";
+        return G16_ERR_OOM;
+    } catch (...) {
+        if (ctx) ctx->c.err = "unknown error"; else g_create_error = "unknown error";
+        return G16_ERR_INVALID;
+    }
+}
+
+static void require(bool ok, const char *what) {
+    if (!ok) throw Error{G16_ERR_INVALID, what};
+}
+
+static Device &single_device(g16_ctx *ctx) {
+    require(ctx->c.devs.size() == 1, "this entry point needs a single-device context");
+    set_device(ctx->c.devs[0].id);
+    return ctx->c.devs[0];
+}
+
+extern "C" {
+
+const char *g16_version(void) { return "groth16-cuda 0.1 (sm_100a)"; }
+
+int g16_device_count(void) {
+#ifndef G16_EMU
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+#else
+    return 1;
+#endif
+}
+
+int g16_ctx_create(const int *devices, int ndev, g16_ctx **out) {
+    if (!out) return G16_ERR_INVALID;
+    *out = nullptr;
+    return guarded(nullptr, [&] {
+#ifndef G16_EMU
+        int count = 0;
+        cudaError_t e = cudaGetDeviceCount(&count);
+        if (e != cudaSuccess || count == 0)
+            throw Error{G16_ERR_NO_DEVICE, std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "count = 0")};
+#else
+        int count = 64;
+#endif
+        std::unique_ptr<g16_ctx> ctx(new g16_ctx);
+        std::vector<int> ids;
+        if (!devices || ndev <= 0) {
+            int cur = 0;
+#ifndef G16_EMU
+            G16_CUDA_CHECK(cudaGetDevice(&cur));
+#endif
+            ids.push_back(cur);
+        } else {
+            ids.assign(devices, devices + ndev);
+        }
+        for (int id : ids) {
+            if (id < 0 || id >= count) throw Error{G16_ERR_NO_DEVICE, "device index out of range"};
+            Device d;
+            d.id = id;
+#ifndef G16_EMU
+            G16_CUDA_CHECK(cudaSetDevice(id));
+            G16_CUDA_CHECK(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
+            d.own_stream = true;
+#endif
+            ctx->c.devs.push_back(std::move(d));
+        }
+        *out = ctx.release();
+    });
+}
+
+void g16_ctx_destroy(g16_ctx *ctx) {
+    if (!ctx) return;
+    for (auto &d : ctx->c.devs) {
+#ifndef G16_EMU
+        cudaSetDevice(d.id);
+        if (d.stream) cudaStreamSynchronize(d.stream);
+#endif
+        d.ws.release();
+#ifndef G16_EMU
+        if (d.own_stream && d.stream) cudaStreamDestroy(d.stream);
+#endif
+    }
+    delete ctx;
+}
+
+const char *g16_last_error(const g16_ctx *ctx) { return ctx ? ctx->c.err.c_str() : g_create_error.c_str(); }
+
+int g16_ctx_set_stream(g16_ctx *ctx, void *cuda_stream) {
+    if (!ctx) return G16_ERR_INVALID;
+    return guarded(ctx, [&] {
+        Device &d = single_device(ctx);
+#ifndef G16_EMU
+        if (d.own_stream && d.stream) { cudaStreamSynchronize(d.stream); cudaStreamDestroy(d.stream); }
+        d.stream = (cudaStream_t)cuda_stream;
+#else
+        d.stream = cuda_stream;
+#endif
+        d.own_stream = false;
+    });
+}
+
+int g16_ctx_synchronize(g16_ctx *ctx) {
+    if (!ctx) return G16_ERR_INVALID;
+    return guarded(ctx, [&] {
+        for (auto &d : ctx->c.devs) { set_device(d.id); stream_sync(d.stream); }
+    });
+}
+
+int g16_ctx_set_window_bits(g16_ctx *ctx, unsigned c) {
+    if (!ctx || c > 24 || c == 1) return G16_ERR_INVALID;
+    ctx->c.c_override = c;
+    return G16_OK;
+}
+
+// ---- bases ------------------------------------------------------------------------------
+extern "C++" {
+template <class F>
+static int bases_upload_impl(g16_ctx *ctx, const uint64_t *xy, const uint8_t *inf, size_t n, g16_bases **out) {
+    if (!ctx || !out) return G16_ERR_INVALID;
+    *out = nullptr;
+    return guarded(ctx, [&] {
+        require(xy || n == 0, "xy is NULL");
+        std::unique_ptr<g16_bases> h(new g16_bases);
+        h->b = bases_upload<F>(&ctx->c, xy, inf, n);
+        *out = h.release();
+    });
+}
+}  // extern "C++"
+int g16_g1_bases_upload(g16_ctx *ctx, const uint64_t *xy, const uint8_t *inf, size_t n, g16_bases **out) {
+    return bases_upload_impl<Fq>(ctx, xy, inf, n, out);
+}
+int g16_g2_bases_upload(g16_ctx *ctx, const uint64_t *xy, const uint8_t *inf, size_t n, g16_bases **out) {
+    return bases_upload_impl<Fq2>(ctx, xy, inf, n, out);
+}
+
+extern "C++" {
+template <class F>
+static int bases_from_device_impl(g16_ctx *ctx, const void *dev_xy, size_t n, g16_bases **out) {
+    if (!ctx || !out) return G16_ERR_INVALID;
+    *out = nullptr;
+    return guarded(ctx, [&] {
+        single_device(ctx);
+        require(dev_xy || n == 0, "dev_xy is NULL");
+        std::unique_ptr<g16_bases> h(new g16_bases);
+        h->b.reset(new Bases);
+        h->b->ctx = &ctx->c; h->b->group = GroupOf<F>::id; h->b->n = n;
+        BasesShard sh;
+        sh.dev = 0; sh.pts = (uint32_t *)dev_xy; sh.begin = 0; sh.n = n; sh.owned = false;
+        h->b->shards.push_back(sh);
+        *out = h.release();
+    });
+}
+}  // extern "C++"
+int g16_g1_bases_from_device(g16_ctx *ctx, const void *dev_xy, size_t n, g16_bases **out) {
+    return bases_from_device_impl<Fq>(ctx, dev_xy, n, out);
+}
+int g16_g2_bases_from_device(g16_ctx *ctx, const void *dev_xy, size_t n, g16_bases **out) {
+    return bases_from_device_impl<Fq2>(ctx, dev_xy, n, out);
+}
+void g16_bases_free(g16_bases *bases) { delete bases; }
+size_t g16_bases_len(const g16_bases *bases) { return bases ? bases->b->n : 0; }
+
+// ---- MSM --------------------------------------------------------------------------------
+extern "C++" {
+template <class F>
+static int msm_impl(g16_ctx *ctx, const g16_bases *bases, const uint64_t *scalars, size_t n, uint64_t *out_xy,
+                    uint8_t *out_inf) {
+    if (!ctx) return G16_ERR_INVALID;
+    return guarded(ctx, [&] {
+        require(bases && out_xy, "NULL argument");
+        require(scalars || n == 0, "scalars is NULL");
+        require(bases->b->ctx == &ctx->c, "bases belong to another context");
+        msm_host<F>(&ctx->c, bases->b.get(), scalars, n, out_xy, out_inf);
+    });
+}
+}  // extern "C++"
+int g16_g1_msm(g16_ctx *ctx, const g16_bases *bases, const uint64_t *scalars, size_t n, uint64_t out_xy[12],
+               uint8_t *out_inf) {
+    return msm_impl<Fq>(ctx, bases, scalars, n, out_xy, out_inf);
+}
+int g16_g2_msm(g16_ctx *ctx, const g16_bases *bases, const uint64_t *scalars, size_t n, uint64_t out_xy[24],
+               uint8_t *out_inf) {
+    return msm_impl<Fq2>(ctx, bases, scalars, n, out_xy, out_inf);
+}
+
+extern "C++" {
+template <class F>
+static int msm_oneshot_impl(g16_ctx *ctx, const uint64_t *xy, const uint8_t *inf, const uint64_t *scalars, size_t n,
+                            uint64_t *out_xy, uint8_t *out_inf) {
+    if (!ctx) return G16_ERR_INVALID;
+    return guarded(ctx, [&] {
+        require(out_xy, "out_xy is NULL");
+        require((xy && scalars) || n == 0, "NULL input");
+        std::unique_ptr<Bases> b = bases_upload<F>(&ctx->c, xy, inf, n);
+        msm_host<F>(&ctx->c, b.get(), scalars, n, out_xy, out_inf);
+    });
+}
+}  // extern "C++"
+int g16_g1_msm_oneshot(g16_ctx *ctx, const uint64_t *xy, const uint8_t *inf, const uint64_t *scalars, size_t n,
+                       uint64_t out_xy[12], uint8_t *out_inf) {
+    return msm_oneshot_impl<Fq>(ctx, xy, inf, scalars, n, out_xy, out_inf);
+}
+int g16_g2_msm_oneshot(g16_ctx *ctx, const uint64_t *xy, const uint8_t *inf, const uint64_t *scalars, size_t n,
+                       uint64_t out_xy[24], uint8_t *out_inf) {
+    return msm_oneshot_impl<Fq2>(ctx, xy, inf, scalars, n, out_xy, out_inf);
+}
+
+extern "C++" {
+template <class F>
+static int msm_device_impl(g16_ctx *ctx, const g16_bases *bases, const void *dev_scalars, size_t n, void *dev_out_affine,
+                           void *dev_out_partial) {
+    if (!ctx) return G16_ERR_INVALID;
+    return guarded(ctx, [&] {
+        Device &dv = single_device(ctx);
+        require(bases && bases->b->ctx == &ctx->c && bases->b->group == GroupOf<F>::id, "bad bases handle");
+        require(bases->b->shards.size() == 1, "bases are sharded");
+        if (n > bases->b->n) throw Error{G16_ERR_LENGTH, "more scalars than bases"};
+        require(dev_scalars || n == 0, "dev_scalars is NULL");
+        msm_run<F>(dv, bases->b->shards[0].pts, (const uint32_t *)dev_scalars, n, true, ctx->c.c_override,
+                   (uint32_t *)dev_out_partial, (uint32_t *)dev_out_affine);
+    });
+}
+}  // extern "C++"
+int g16_g1_msm_device(g16_ctx *ctx, const g16_bases *bases, const void *dev_scalars, size_t n, void *dev_out_affine,
+                      void *dev_out_partial) {
+    return msm_device_impl<Fq>(ctx, bases, dev_scalars, n, dev_out_affine, dev_out_partial);
+}
+int g16_g2_msm_device(g16_ctx *ctx, const g16_bases *bases, const void *dev_scalars, size_t n, void *dev_out_affine,
+                      void *dev_out_partial) {
+    return msm_device_impl<Fq2>(ctx, bases, dev_scalars, n, dev_out_affine, dev_out_partial);
+}
+
+extern "C++" {
+template <class F>
+static int combine_impl(g16_ctx *ctx, const void *dev_partials, size_t k, void *dev_out_affine) {
+    if (!ctx) return G16_ERR_INVALID;
+    return guarded(ctx, [&] {
+        Device &dv = single_device(ctx);
+        require(dev_out_affine && (dev_partials || k == 0), "NULL argument");
+        k_partial_combine<F>(dv.stream, (const uint32_t *)dev_partials, (uint32_t)k, nullptr, (uint32_t *)dev_out_affine);
+    });
+}
+}  // extern "C++"
+int g16_g1_combine_partials_device(g16_ctx *ctx, const void *dev_partials, size_t k, void *dev_out_affine) {
+    return combine_impl<Fq>(ctx, dev_partials, k, dev_out_affine);
+}
+int g16_g2_combine_partials_device(g16_ctx *ctx, const void *dev_partials, size_t k, void *dev_out_affine) {
+    return combine_impl<Fq2>(ctx, dev_partials, k, dev_out_affine);
+}
+
+// ---- fixed base ---------------------------------------------------------------------------
+extern "C++" {
+template <class F>
+static int fixed_base_impl(g16_ctx *ctx, const uint64_t *base_xy, const uint64_t *scalars, size_t n, uint64_t *out_xy,
+                           uint8_t *out_inf) {
+    if (!ctx) return G16_ERR_INVALID;
+    return guarded(ctx, [&] {
+        require(base_xy && (n == 0 || (scalars && out_xy)), "NULL argument");
+        fixed_base_host<F>(&ctx->c, base_xy, scalars, n, out_xy, out_inf);
+    });
+}
+}  // extern "C++"
+int g16_g1_fixed_base_mul(g16_ctx *ctx, const uint64_t base_xy[12], const uint64_t *scalars, size_t n,
+                          uint64_t *out_xy, uint8_t *out_inf) {
+    return fixed_base_impl<Fq>(ctx, base_xy, scalars, n, out_xy, out_inf);
+}
+int g16_g2_fixed_base_mul(g16_ctx *ctx, const uint64_t base_xy[24], const uint64_t *scalars, size_t n,
+                          uint64_t *out_xy, uint8_t *out_inf) {
+    return fixed_base_impl<Fq2>(ctx, base_xy, scalars, n, out_xy, out_inf);
+}
+extern "C++" {
+template <class F>
+static int fixed_base_device_impl(g16_ctx *ctx, const uint64_t *base_xy, const void *dev_scalars, size_t n,
+                                  void *dev_out_xy) {
+    if (!ctx) return G16_ERR_INVALID;
+    return guarded(ctx, [&] {
+        Device &dv = single_device(ctx);
+        require(base_xy && (n == 0 || (dev_scalars && dev_out_xy)), "NULL argument");
+        fixed_base_device<F>(dv, base_xy, (const uint32_t *)dev_scalars, n, (uint32_t *)dev_out_xy);
+    });
+}
+}  // extern "C++"
+int g16_g1_fixed_base_mul_device(g16_ctx *ctx, const uint64_t base_xy[12], const void *dev_scalars, size_t n,
+                                 void *dev_out_xy) {
+    return fixed_base_device_impl<Fq>(ctx, base_xy, dev_scalars, n, dev_out_xy);
+}
+int g16_g2_fixed_base_mul_device(g16_ctx *ctx, const uint64_t base_xy[24], const void *dev_scalars, size_t n,
+                                 void *dev_out_xy) {
+    return fixed_base_device_impl<Fq2>(ctx, base_xy, dev_scalars, n, dev_out_xy);
+}
+
+// ---- proving key + prove schedule --------------------------------------------------------------
+// Concatenate `k` single points (host) in front of a host array and upload.
+extern "C++" {
+template <class F>
+static std::unique_ptr<Bases> upload_with_prefix(Context *c, std::initializer_list<const uint64_t *> singles,
+                                                 const uint64_t *xy, const uint8_t *inf, size_t n) {
+    constexpr size_t PW = FieldWords<F>::N;  // u64 words per point
+    size_t k = singles.size();
+    std::vector<uint64_t> buf((k + n) * PW);
+    std::vector<uint8_t> flags(k + n, 0);
+    size_t i = 0;
+    for (const uint64_t *p : singles) {
+        memcpy(buf.data() + i * PW, p, PW * 8);
+        // a single point at infinity is passed as all-zero coordinates
+        bool z = true;
+        for (size_t j = 0; j < PW; ++j) z = z && p[j] == 0;
+        flags[i] = z;
+        ++i;
+    }
+    if (n) memcpy(buf.data() + k * PW, xy, n * PW * 8);
+    if (inf) memcpy(flags.data() + k, inf, n);
+    return bases_upload<F>(c, buf.data(), flags.data(), k + n);
+}
+}  // extern "C++"
+
+int g16_pk_upload(g16_ctx *ctx, const g16_pk_host *pk, g16_pk **out) {
+    if (!ctx || !pk || !out) return G16_ERR_INVALID;
+    *out = nullptr;
+    return guarded(ctx, [&] {
+        require(pk->alpha_g1 && pk->beta_g1 && pk->delta_g1 && pk->beta_g2 && pk->delta_g2, "NULL single point");
+        std::unique_ptr<g16_pk> h(new g16_pk);
+        h->ctx = &ctx->c;
+        h->a = upload_with_prefix<Fq>(&ctx->c, {pk->alpha_g1, pk->delta_g1}, pk->a_g1, pk->a_g1_inf, pk->a_len);
+        h->b2 = upload_with_prefix<Fq2>(&ctx->c, {pk->beta_g2, pk->delta_g2}, pk->b_g2, pk->b_g2_inf, pk->b2_len);
+        h->b1 = upload_with_prefix<Fq>(&ctx->c, {pk->beta_g1}, pk->b_g1, pk->b_g1_inf, pk->b1_len);
+        h->ic = upload_with_prefix<Fq>(&ctx->c, {}, pk->ic_g1, pk->ic_g1_inf, pk->ic_len);
+        h->h = upload_with_prefix<Fq>(&ctx->c, {}, pk->h_g1, pk->h_g1_inf, pk->h_len);
+        h->a_len = pk->a_len; h->b1_len = pk->b1_len; h->b2_len = pk->b2_len; h->ic_len = pk->ic_len; h->h_len = pk->h_len;
+        h->num_public = pk->num_public;
+        *out = h.release();
+    });
+}
+void g16_pk_free(g16_pk *pk) { delete pk; }
+
+static const uint64_t FR_ONE_MONT[4] = {0x00000001fffffffeULL, 0x5884b7fa00034802ULL, 0x998c4fefecbc4ff5ULL,
+                                        0x1824b159acc5056fULL};
+
+// The MSM schedule of Prover::prove (crates/groth16-core/src/lib.rs:164-271).  The reference
+// builds fresh (scalar, point) lists with zero scalars filtered out; here the CRS arrays stay
+// resident, the unfiltered scalar vectors are sent (a zero scalar contributes no digit) and the
+// ad-hoc terms (alpha, r*delta, ...) ride along as extra entries -- the sums are the same group
+// elements.
+int g16_prove(g16_ctx *ctx, const g16_pk *pk, const uint64_t *assignment_fr, size_t num_vars, const uint64_t *h_coeffs,
+              size_t num_h, const uint64_t r[4], const uint64_t s[4], uint64_t a_xy[12], uint8_t *a_inf,
+              uint64_t b_xy[24], uint8_t *b_inf, uint64_t c_xy[12], uint8_t *c_inf) {
+    if (!ctx) return G16_ERR_INVALID;
+    return guarded(ctx, [&] {
+        require(pk && pk->ctx == &ctx->c, "bad pk handle");
+        require(assignment_fr && r && s && a_xy && b_xy && c_xy, "NULL argument");
+        require(num_vars > pk->num_public, "assignment shorter than the public inputs");
+        Context *c = &ctx->c;
+        auto put = [](std::vector<uint64_t> &v, const uint64_t *x) { v.insert(v.end(), x, x + 4); };
+        uint8_t inf_a = 0, inf_b = 0, inf_b1 = 0, inf_h = 1, inf_c = 0;
+
+        // pi_A = alpha + sum w_i a_i + r delta                                        (lib.rs:164-179)
+        size_t na = std::min(num_vars, pk->a_len);
+        std::vector<uint64_t> sc;
+        sc.reserve((na + 2) * 4);
+        put(sc, FR_ONE_MONT); put(sc, r);
+        sc.insert(sc.end(), assignment_fr, assignment_fr + na * 4);
+        msm_host<Fq>(c, pk->a.get(), sc.data(), na + 2, a_xy, &inf_a);
+
+        // pi_B = beta + sum w_i b_i + s delta  (G2)                                   (lib.rs:182-197)
+        size_t nb2 = std::min(num_vars, pk->b2_len);
+        sc.clear();
+        put(sc, FR_ONE_MONT); put(sc, s);
+        sc.insert(sc.end(), assignment_fr, assignment_fr + nb2 * 4);
+        msm_host<Fq2>(c, pk->b2.get(), sc.data(), nb2 + 2, b_xy, &inf_b);
+
+        // [H(s)]_1                                                                      (lib.rs:211-221)
+        uint64_t h_xy[12] = {0};
+        size_t nh = h_coeffs ? std::min(num_h, pk->h_len) : 0;
+        if (nh) msm_host<Fq>(c, pk->h.get(), h_coeffs, nh, h_xy, &inf_h);
+
+        // pi_B' = beta_1 + sum w_i b_g1[i]                                              (lib.rs:246-255)
+        size_t nb1 = std::min(num_vars, pk->b1_len);
+        uint64_t b1_xy[12];
+        sc.clear();
+        put(sc, FR_ONE_MONT);
+        sc.insert(sc.end(), assignment_fr, assignment_fr + nb1 * 4);
+        msm_host<Fq>(c, pk->b1.get(), sc.data(), nb1 + 1, b1_xy, &inf_b1);
+
+        // pi_C = sum_{private} w_i ic_i + H + s pi_A + r pi_B'                          (lib.rs:224-265)
+        size_t first_priv = pk->num_public + 1;
+        size_t nic = num_vars > first_priv ? std::min(num_vars - first_priv, pk->ic_len) : 0;
+        uint64_t cm_xy[12] = {0};
+        uint8_t inf_cm = 1;
+        if (nic) msm_host<Fq>(c, pk->ic.get(), assignment_fr + first_priv * 4, nic, cm_xy, &inf_cm);
+        uint64_t adhoc_xy[4 * 12];
+        uint8_t adhoc_inf[4] = {inf_cm, inf_h, inf_a, inf_b1};
+        memcpy(adhoc_xy, cm_xy, 96); memcpy(adhoc_xy + 12, h_xy, 96); memcpy(adhoc_xy + 24, a_xy, 96); memcpy(adhoc_xy + 36, b1_xy, 96);
+        sc.clear();
+        put(sc, FR_ONE_MONT); put(sc, FR_ONE_MONT); put(sc, s); put(sc, r);
+        {
+            std::unique_ptr<Bases> adhoc = bases_upload<Fq>(c, adhoc_xy, adhoc_inf, 4);
+            msm_host<Fq>(c, adhoc.get(), sc.data(), 4, c_xy, &inf_c);
+        }
+        if (a_inf) *a_inf = inf_a;
+        if (b_inf) *b_inf = inf_b;
+        if (c_inf) *c_inf = inf_c;
+    });
+}
+
+}  // extern "C"

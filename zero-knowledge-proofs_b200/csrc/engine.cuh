@@ -1,0 +1,281 @@
+// Host-side engine: contexts, resident bases, the MSM pipeline and the fixed-base pipeline.
+// Everything here only allocates, copies and launches; all arithmetic runs in the kernels.
+#pragma once
+#include <algorithm>
+#include <memory>
+#include <vector>
+#include "kernel_api.cuh"
+
+namespace g16 {
+
+enum Group { GROUP_G1 = 1, GROUP_G2 = 2 };
+
+template <class F> struct GroupOf { static constexpr int id = FieldWords<F>::group; };
+
+struct Workspace {
+    DevBuf scalars, counts, cursor, entries, buckets, red[4], scan_tmp, out, partials, staging;
+    DevBuf fb_base, fb_powers, fb_table[3], fb_out, fb_flags;
+    std::vector<uint32_t> fb_table_key[3];  // base limbs the cached table was built for
+    void release() {
+        scalars.release(); counts.release(); cursor.release(); entries.release(); buckets.release();
+        for (auto &r : red) r.release();
+        scan_tmp.release(); out.release(); partials.release(); staging.release();
+        fb_base.release(); fb_powers.release(); fb_out.release(); fb_flags.release();
+        for (auto &t : fb_table) t.release();
+    }
+};
+
+struct Device {
+    int id = 0;
+    stream_t stream = nullptr;
+    bool own_stream = false;
+    Workspace ws;
+};
+
+inline void set_device(int id) {
+#ifndef G16_EMU
+    G16_CUDA_CHECK(cudaSetDevice(id));
+#else
+    (void)id;
+#endif
+}
+
+struct Context {
+    std::vector<Device> devs;
+    std::string err;
+    unsigned c_override = 0;
+};
+
+struct BasesShard {
+    int dev = 0;  // index into Context::devs
+    uint32_t *pts = nullptr;
+    size_t begin = 0, n = 0;
+    bool owned = true;
+};
+
+struct Bases {
+    Context *ctx = nullptr;
+    int group = 0;
+    size_t n = 0;
+    std::vector<BasesShard> shards;
+    ~Bases() {
+        for (auto &s : shards)
+            if (s.owned && s.pts) { set_device(ctx->devs[s.dev].id); dev_free(s.pts); }
+    }
+};
+
+// ---------------------------------------------------------------------------------------
+// Window size.  Cost model in field multiplications: every non-zero digit costs one mixed
+// addition (10 M), every bucket costs two full additions in the reduction (2 x 14 M).
+// ---------------------------------------------------------------------------------------
+inline MsmPlan make_plan(size_t n, unsigned c_override, size_t point_words) {
+    unsigned best_c = 1;
+    double best = 1e300;
+    unsigned lo = 2, hi = 22;
+    if (c_override) lo = hi = std::min(std::max(c_override, 2u), 24u);
+    for (unsigned c = lo; c <= hi; ++c) {
+        double nwin = (256 + c - 1) / c;
+        double nb = (double)(1ull << (c - 1));
+        // bucket storage cap: 8 GiB
+        if (!c_override && nwin * nb * 2.0 * point_words * 4.0 > 8.0 * 1073741824.0) break;
+        double cost = nwin * ((double)n * 10.0 + nb * 30.0);
+        if (cost < best) { best = cost; best_c = c; }
+    }
+    MsmPlan p;
+    p.c = best_c;
+    p.nwin = (256 + best_c - 1) / best_c;
+    p.nb = 1u << (best_c - 1);
+    p.total = p.nwin * p.nb;
+    return p;
+}
+
+constexpr uint32_t REDUCE_L = 32;  // group size of one reduction level
+constexpr uint32_t REDUCE_LOG_L = 5;
+
+// One MSM on one device, asynchronous on dv.stream.
+//   pts        : packed affine bases on this device (n points)
+//   d_scalars  : n x 8 u32 on this device
+//   d_out_xyzz : 4*FieldWords<F>::N words (may be null), d_out_aff : 2*FieldWords<F>::N + 1 words (may be null)
+template <class F>
+void msm_run(Device &dv, const uint32_t *pts, const uint32_t *d_scalars, size_t n, bool mont, unsigned c_override,
+             uint32_t *d_out_xyzz, uint32_t *d_out_aff) {
+    stream_t s = dv.stream;
+    Workspace &ws = dv.ws;
+    if (n == 0) {
+        k_partial_combine<F>(s, nullptr, 0u, d_out_xyzz, d_out_aff);
+        return;
+    }
+    if (n >= (1ull << 31)) throw Error{G16_ERR_INVALID, "MSM length must be < 2^31"};
+    MsmPlan plan = make_plan(n, c_override, 2 * FieldWords<F>::N);
+    size_t total = plan.total;
+    if ((double)n * plan.nwin >= 4294967295.0) throw Error{G16_ERR_INVALID, "n * windows exceeds 2^32 entries"};
+
+    // 1. bucket sizes
+    uint32_t *counts = ws.counts.as<uint32_t>(total + 1);
+    dev_memset(counts, 0, (total + 1) * sizeof(uint32_t), s);
+    k_digit_count(s, n, d_scalars, mont, plan, counts);
+    // 2. bucket offsets (exclusive scan; offsets[total] = number of entries)
+    uint32_t *scan_tmp = ws.scan_tmp.as<uint32_t>(k_scan_tmp_words(total + 1));
+    k_exclusive_scan(s, counts, counts, total + 1, scan_tmp);
+    uint32_t *offsets = counts;
+    // 3. scatter (point index, sign) into bucket order
+    uint32_t *cursor = ws.cursor.as<uint32_t>(total);
+    copy_d2d(cursor, offsets, total * sizeof(uint32_t), s);
+    uint32_t *entries = ws.entries.as<uint32_t>(n * plan.nwin);
+    k_digit_scatter(s, n, d_scalars, mont, plan, cursor, entries);
+    // 4. bucket accumulation (the hot kernel)
+    uint32_t *buckets = ws.buckets.as<uint32_t>(total * 4 * FieldWords<F>::N);
+    k_accumulate<F>(s, total, pts, entries, offsets, buckets);
+    // 5. parallel bucket reduction
+    const uint32_t *X = buckets, *Y = nullptr;
+    uint32_t n_in = plan.nb, level = 0;
+    int flip = 0;
+    while (n_in > 1) {
+        uint32_t n_out = (n_in + REDUCE_L - 1) / REDUCE_L;
+        uint32_t *Xo = ws.red[flip].as<uint32_t>((size_t)plan.nwin * n_out * 4 * FieldWords<F>::N);
+        uint32_t *Yo = ws.red[flip + 1].as<uint32_t>((size_t)plan.nwin * n_out * 4 * FieldWords<F>::N);
+        k_reduce_level<F>(s, (size_t)plan.nwin * n_out, X, Y, n_in, n_out, REDUCE_L, REDUCE_LOG_L * level, Xo, Yo);
+        X = Xo; Y = Yo;
+        n_in = n_out; ++level; flip ^= 2;
+    }
+    // 6. window fold + to affine
+    k_window_combine<F>(s, X, Y, plan.nwin, plan.c, d_out_xyzz, d_out_aff);
+}
+
+// Import host points (ark layout + infinity bytes) into a device shard.
+template <class F>
+uint32_t *import_points(Device &dv, const uint64_t *xy, const uint8_t *inf, size_t n) {
+    set_device(dv.id);
+    stream_t s = dv.stream;
+    size_t words = n * 2 * FieldWords<F>::N;
+    uint32_t *pts = (uint32_t *)dev_alloc(words * 4);
+    try {
+        if (!inf) {
+            copy_h2d(pts, xy, words * 4, s);
+        } else {
+            uint32_t *stage = dv.ws.staging.as<uint32_t>(words + (n + 3) / 4 + 4);
+            uint8_t *d_inf = (uint8_t *)(stage + words);
+            copy_h2d(stage, xy, words * 4, s);
+            copy_h2d(d_inf, inf, n, s);
+            k_import_bases<F>(s, n, stage, d_inf, pts);
+        }
+        stream_sync(s);
+    } catch (...) {
+        dev_free(pts);
+        throw;
+    }
+    return pts;
+}
+
+template <class F>
+std::unique_ptr<Bases> bases_upload(Context *ctx, const uint64_t *xy, const uint8_t *inf, size_t n) {
+    std::unique_ptr<Bases> b(new Bases);
+    b->ctx = ctx; b->group = GroupOf<F>::id; b->n = n;
+    size_t ndev = ctx->devs.size();
+    for (size_t d = 0; d < ndev; ++d) {
+        size_t begin = n * d / ndev, end = n * (d + 1) / ndev;
+        BasesShard sh;
+        sh.dev = (int)d; sh.begin = begin; sh.n = end - begin; sh.owned = true;
+        sh.pts = import_points<F>(ctx->devs[d], xy + begin * (FieldWords<F>::N), inf ? inf + begin : nullptr, sh.n);
+        b->shards.push_back(sh);
+    }
+    return b;
+}
+
+// Host scalars -> host affine result over all shards of `bases`.
+template <class F>
+void msm_host(Context *ctx, const Bases *bases, const uint64_t *scalars, size_t n, uint64_t *out_xy, uint8_t *out_inf) {
+    if (bases->group != GroupOf<F>::id) throw Error{G16_ERR_INVALID, "bases belong to the other group"};
+    if (n > bases->n) throw Error{G16_ERR_LENGTH, "more scalars than bases (ark: Err(min_len))"};
+    constexpr size_t PW = 4 * FieldWords<F>::N, AW = 2 * FieldWords<F>::N + 1;
+    Device &d0 = ctx->devs[0];
+    size_t nsh = bases->shards.size();
+    // launch every shard (asynchronous), then gather the partials on device 0
+    std::vector<uint32_t> host_partials(nsh * PW);
+    for (size_t k = 0; k < nsh; ++k) {
+        const BasesShard &sh = bases->shards[k];
+        Device &dv = ctx->devs[sh.dev];
+        set_device(dv.id);
+        size_t lo = std::min(sh.begin, n), hi = std::min(sh.begin + sh.n, n);
+        size_t cnt = hi - lo;
+        uint32_t *d_sc = dv.ws.scalars.as<uint32_t>(cnt * 8 + 8);
+        copy_h2d(d_sc, scalars + lo * 4, cnt * 32, dv.stream);
+        uint32_t *d_out = dv.ws.out.as<uint32_t>(PW + AW);
+        if (nsh == 1) {
+            msm_run<F>(dv, sh.pts, d_sc, cnt, true, ctx->c_override, nullptr, d_out + PW);
+        } else {
+            msm_run<F>(dv, sh.pts, d_sc, cnt, true, ctx->c_override, d_out, nullptr);
+            copy_d2h(host_partials.data() + k * PW, d_out, PW * 4, dv.stream);
+        }
+    }
+    uint32_t aff[AW];
+    set_device(d0.id);
+    if (nsh == 1) {
+        copy_d2h(aff, (uint32_t *)d0.ws.out.p + PW, AW * 4, d0.stream);
+        stream_sync(d0.stream);
+    } else {
+        for (size_t k = 0; k < nsh; ++k) { set_device(ctx->devs[bases->shards[k].dev].id); stream_sync(ctx->devs[bases->shards[k].dev].stream); }
+        set_device(d0.id);
+        uint32_t *d_part = d0.ws.partials.as<uint32_t>(nsh * PW + AW);
+        copy_h2d(d_part, host_partials.data(), nsh * PW * 4, d0.stream);
+        k_partial_combine<F>(d0.stream, d_part, (uint32_t)nsh, nullptr, d_part + nsh * PW);
+        copy_d2h(aff, d_part + nsh * PW, AW * 4, d0.stream);
+        stream_sync(d0.stream);
+    }
+    memcpy(out_xy, aff, (AW - 1) * 4);
+    if (out_inf) *out_inf = (uint8_t)aff[AW - 1];
+}
+
+// ---------------------------------------------------------------------------------------
+// fixed base
+// ---------------------------------------------------------------------------------------
+template <class F>
+const uint32_t *fixed_base_table(Device &dv, const uint64_t *base_xy) {
+    constexpr int slot = GroupOf<F>::id;
+    Workspace &ws = dv.ws;
+    stream_t s = dv.stream;
+    const uint32_t *key = (const uint32_t *)base_xy;
+    std::vector<uint32_t> &cached = ws.fb_table_key[slot];
+    if (cached.size() == 2 * FieldWords<F>::N && memcmp(cached.data(), key, 2 * FieldWords<F>::N * 4) == 0 && ws.fb_table[slot].p)
+        return (const uint32_t *)ws.fb_table[slot].p;
+    uint32_t *d_base = ws.fb_base.as<uint32_t>(2 * FieldWords<F>::N);
+    copy_h2d(d_base, base_xy, 2 * FieldWords<F>::N * 4, s);
+    uint32_t *powers = ws.fb_powers.as<uint32_t>(FB_WINDOWS * 4 * FieldWords<F>::N);
+    k_fb_powers<F>(s, d_base, powers);
+    uint32_t *table = ws.fb_table[slot].as<uint32_t>((size_t)FB_WINDOWS * FB_ENTRIES * 2 * FieldWords<F>::N);
+    k_fb_table<F>(s, powers, table);
+    cached.assign(key, key + 2 * FieldWords<F>::N);
+    return table;
+}
+
+template <class F>
+void fixed_base_device(Device &dv, const uint64_t *base_xy, const uint32_t *d_scalars, size_t n, uint32_t *d_out) {
+    const uint32_t *table = fixed_base_table<F>(dv, base_xy);
+    k_fb_mul<F>(dv.stream, n, d_scalars, true, table, d_out);
+}
+
+template <class F>
+void fixed_base_host(Context *ctx, const uint64_t *base_xy, const uint64_t *scalars, size_t n, uint64_t *out_xy,
+                     uint8_t *out_inf) {
+    size_t ndev = ctx->devs.size();
+    constexpr size_t W = 2 * FieldWords<F>::N;
+    for (size_t d = 0; d < ndev; ++d) {
+        Device &dv = ctx->devs[d];
+        set_device(dv.id);
+        size_t lo = n * d / ndev, hi = n * (d + 1) / ndev, cnt = hi - lo;
+        if (!cnt) continue;
+        uint32_t *d_sc = dv.ws.scalars.as<uint32_t>(cnt * 8);
+        copy_h2d(d_sc, scalars + lo * 4, cnt * 32, dv.stream);
+        uint32_t *d_out = dv.ws.fb_out.as<uint32_t>(cnt * W);
+        fixed_base_device<F>(dv, base_xy, d_sc, cnt, d_out);
+        copy_d2h(out_xy + lo * (W / 2), d_out, cnt * W * 4, dv.stream);
+        if (out_inf) {
+            uint8_t *d_fl = dv.ws.fb_flags.as<uint8_t>(cnt);
+            k_export_flags<F>(dv.stream, cnt, d_out, d_fl);
+            copy_d2h(out_inf + lo, d_fl, cnt, dv.stream);
+        }
+    }
+    for (size_t d = 0; d < ndev; ++d) { set_device(ctx->devs[d].id); stream_sync(ctx->devs[d].stream); }
+}
+
+}  // namespace g16

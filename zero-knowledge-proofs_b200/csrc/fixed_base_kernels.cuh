@@ -1,0 +1,87 @@
+// Fixed-base batch scalar multiplication for CRS generation.
+//
+// Replaces the `par_iter().map(|v| (g1_gen * fr).into_affine())` blocks of
+// /root/reference/crates/groth16-setup/src/lib.rs:185-241 (and the six single muls at :166-171):
+// ark does an independent double-and-add plus one inversion per element; here the base gets a
+// window table (FB_WINDOWS windows of FB_BITS bits, affine entries, L2 resident) and every scalar
+// costs at most FB_WINDOWS mixed additions, followed by a to-affine step.
+#pragma once
+#include "msm_kernels.cuh"
+
+namespace g16 {
+
+
+// powers[j] = 2^(FB_BITS * j) * base  (XYZZ), one thread
+template <class F>
+struct FbPowers {
+    static constexpr int BLOCK = 32;
+    G16_HD static void run(size_t, const uint32_t *base_xy, uint32_t *powers) {
+        Affine<F> b = load_affine<F>(base_xy, 0);
+        XYZZ<F> acc = XYZZ<F>::from_affine(b);
+        for (uint32_t j = 0; j < FB_WINDOWS; ++j) {
+            store_xyzz<F>(powers, j, acc);
+            for (uint32_t s = 0; s < FB_BITS; ++s) xyzz_dbl(acc);
+        }
+    }
+};
+
+template <class F>
+G16_HD void store_affine(uint32_t *dst, size_t idx, const Affine<F> &a) {
+    const uint32_t *s = reinterpret_cast<const uint32_t *>(&a);
+    uint32_t *d = dst + idx * (2 * F::N);
+#if G16_DEVICE_CODE
+    uint4 *d4 = reinterpret_cast<uint4 *>(d);
+#pragma unroll
+    for (int j = 0; j < F::N / 2; ++j) d4[j] = make_uint4(s[4 * j], s[4 * j + 1], s[4 * j + 2], s[4 * j + 3]);
+#else
+    for (int j = 0; j < 2 * F::N; ++j) d[j] = s[j];
+#endif
+}
+
+// table[j * FB_ENTRIES + (d - 1)] = d * powers[j], affine.  One thread per entry.
+template <class F>
+struct FbTable {
+    static constexpr int BLOCK = 64;
+    G16_HD static void run(size_t t, const uint32_t *powers, uint32_t *table) {
+        uint32_t j = (uint32_t)(t / FB_ENTRIES), d = (uint32_t)(t % FB_ENTRIES) + 1u;
+        XYZZ<F> p = load_xyzz<F>(powers, j);
+        XYZZ<F> acc = XYZZ<F>::inf();
+        for (int bit = (int)FB_BITS - 1; bit >= 0; --bit) {
+            xyzz_dbl(acc);
+            if ((d >> bit) & 1u) xyzz_add(acc, p);
+        }
+        store_affine<F>(table, t, xyzz_to_affine(acc));
+    }
+};
+
+// out[i] = scalar_i * base as a packed affine point ((0,0) = infinity).  One thread per scalar.
+template <class F>
+struct FbMul {
+    static constexpr int BLOCK = 128;
+    G16_HD static void run(size_t i, const uint32_t *scalars, bool mont, const uint32_t *table, uint32_t *out) {
+        uint32_t k[8];
+        load_scalar(scalars, i, mont, k);
+        XYZZ<F> acc = XYZZ<F>::inf();
+        for (uint32_t j = 0; j < FB_WINDOWS; ++j) {
+            uint32_t d = (k[j >> 2] >> ((j & 3u) * 8u)) & 0xffu;
+            if (d) {
+                Affine<F> p = load_affine<F>(table, (size_t)j * FB_ENTRIES + (d - 1u));
+                xyzz_madd(acc, p.x, p.y);
+            }
+        }
+        store_affine<F>(out, i, xyzz_to_affine(acc));
+    }
+};
+
+// packed device points -> host layout helper: infinity flags from the (0,0) encoding
+template <class F>
+struct ExportFlags {
+    static constexpr int BLOCK = 256;
+    G16_HD static void run(size_t i, const uint32_t *pts, uint8_t *inf) {
+        uint32_t v = 0;
+        for (int j = 0; j < 2 * F::N; ++j) v |= pts[i * (2 * F::N) + j];
+        inf[i] = v == 0 ? 1 : 0;
+    }
+};
+
+}  // namespace g16

@@ -1,0 +1,59 @@
+// Host-callable launchers of the kernels, one declaration per kernel.  The definitions live
+// in kernel_impl.cuh and are explicitly instantiated in the k_*.cu translation units so that
+// the big kernels compile in parallel (and the cold ones with out-of-line field multiplies).
+#pragma once
+#include "rt.cuh"
+
+namespace g16 {
+
+struct MsmPlan {
+    uint32_t c;        // window bits
+    uint32_t nwin;     // number of windows = ceil(256 / c)
+    uint32_t nb;       // buckets per window = 2^(c-1)
+    uint32_t total;    // nwin * nb
+};
+
+template <class P> struct Fp;
+struct FqParams;
+struct Fq2;
+using Fq = Fp<FqParams>;
+
+// u32 words of one coordinate
+template <class F> struct FieldWords;
+template <> struct FieldWords<Fq> { static constexpr size_t N = 12; static constexpr int group = 1; };
+template <> struct FieldWords<Fq2> { static constexpr size_t N = 24; static constexpr int group = 2; };
+
+// scalars -> bucket histogram / bucket-ordered entries
+void k_digit_count(stream_t s, size_t n, const uint32_t *scalars, bool mont, MsmPlan plan, uint32_t *counts);
+void k_digit_scatter(stream_t s, size_t n, const uint32_t *scalars, bool mont, MsmPlan plan, uint32_t *cursor,
+                     uint32_t *entries);
+size_t k_scan_tmp_words(size_t n);
+void k_exclusive_scan(stream_t s, const uint32_t *in, uint32_t *out, size_t n, uint32_t *tmp);
+
+template <class F>
+void k_accumulate(stream_t s, size_t items, const uint32_t *pts, const uint32_t *entries, const uint32_t *offsets,
+                  uint32_t *buckets);
+template <class F>
+void k_reduce_level(stream_t s, size_t threads, const uint32_t *X, const uint32_t *Y, uint32_t n_in, uint32_t n_out,
+                    uint32_t L, uint32_t shift, uint32_t *Xo, uint32_t *Yo);
+template <class F>
+void k_window_combine(stream_t s, const uint32_t *X, const uint32_t *Y, uint32_t nwin, uint32_t c, uint32_t *out_xyzz,
+                      uint32_t *out_aff);
+template <class F>
+void k_partial_combine(stream_t s, const uint32_t *partials, uint32_t k, uint32_t *out_xyzz, uint32_t *out_aff);
+template <class F>
+void k_import_bases(stream_t s, size_t n, const uint32_t *xy, const uint8_t *inf, uint32_t *pts);
+template <class F>
+void k_export_flags(stream_t s, size_t n, const uint32_t *pts, uint8_t *inf);
+
+constexpr uint32_t FB_BITS = 8;
+constexpr uint32_t FB_WINDOWS = 256 / FB_BITS;         // 32
+constexpr uint32_t FB_ENTRIES = (1u << FB_BITS) - 1u;  // 255 non-zero digits per window
+template <class F>
+void k_fb_powers(stream_t s, const uint32_t *base_xy, uint32_t *powers);
+template <class F>
+void k_fb_table(stream_t s, const uint32_t *powers, uint32_t *table);
+template <class F>
+void k_fb_mul(stream_t s, size_t n, const uint32_t *scalars, bool mont, const uint32_t *table, uint32_t *out);
+
+}  // namespace g16

@@ -1,0 +1,49 @@
+// Definitions of the launchers declared in kernel_api.cuh (see there).
+#pragma once
+#include "kernel_api.cuh"
+#include "fixed_base_kernels.cuh"
+#include "msm_kernels.cuh"
+
+namespace g16 {
+
+template <class F>
+void k_accumulate(stream_t s, size_t items, const uint32_t *pts, const uint32_t *entries, const uint32_t *offsets,
+                  uint32_t *buckets) {
+    launch<BucketAccumulate<F>>(items, s, pts, entries, offsets, buckets);
+}
+template <class F>
+void k_reduce_level(stream_t s, size_t threads, const uint32_t *X, const uint32_t *Y, uint32_t n_in, uint32_t n_out,
+                    uint32_t L, uint32_t shift, uint32_t *Xo, uint32_t *Yo) {
+    launch<ReduceLevel<F>>(threads, s, X, Y, n_in, n_out, L, shift, Xo, Yo);
+}
+template <class F>
+void k_window_combine(stream_t s, const uint32_t *X, const uint32_t *Y, uint32_t nwin, uint32_t c, uint32_t *out_xyzz,
+                      uint32_t *out_aff) {
+    launch<WindowCombine<F>>(1, s, X, Y, nwin, c, out_xyzz, out_aff);
+}
+template <class F>
+void k_partial_combine(stream_t s, const uint32_t *partials, uint32_t k, uint32_t *out_xyzz, uint32_t *out_aff) {
+    launch<PartialCombine<F>>(1, s, partials, k, out_xyzz, out_aff);
+}
+template <class F>
+void k_import_bases(stream_t s, size_t n, const uint32_t *xy, const uint8_t *inf, uint32_t *pts) {
+    launch<ImportBases<F>>(n, s, xy, inf, pts);
+}
+template <class F>
+void k_export_flags(stream_t s, size_t n, const uint32_t *pts, uint8_t *inf) {
+    launch<ExportFlags<F>>(n, s, pts, inf);
+}
+template <class F>
+void k_fb_powers(stream_t s, const uint32_t *base_xy, uint32_t *powers) {
+    launch<FbPowers<F>>(1, s, base_xy, powers);
+}
+template <class F>
+void k_fb_table(stream_t s, const uint32_t *powers, uint32_t *table) {
+    launch<FbTable<F>>((size_t)FB_WINDOWS * FB_ENTRIES, s, powers, table);
+}
+template <class F>
+void k_fb_mul(stream_t s, size_t n, const uint32_t *scalars, bool mont, const uint32_t *table, uint32_t *out) {
+    launch<FbMul<F>>(n, s, scalars, mont, table, out);
+}
+
+}  // namespace g16

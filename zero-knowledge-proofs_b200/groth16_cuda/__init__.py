@@ -1,0 +1,337 @@
+"""groth16_cuda -- Python host binding of libg16cuda.so (the B200 MSM engine).
+
+This mirrors the Rust `groth16-cuda` crate (../rust/groth16-cuda) one to one: it only marshals
+ark-layout limbs (numpy uint64) across the C ABI of include/g16_cuda.h.  Names follow the
+reference seam:
+
+    Context.multi_scalar_mult_g1 / _g2   <- Prover::multi_scalar_mult_g1/_g2
+                                            (/root/reference/crates/groth16-core/src/lib.rs:275-300)
+    Context.fixed_base_mul_g1 / _g2      <- `(gen * fr).into_affine()` blocks of
+                                            CRS::generate_from_qap (crates/groth16-setup/src/lib.rs:185-241)
+    Context.prove                        <- group part of Prover::prove (lib.rs:164-271)
+
+There is no CPU fallback: importing works anywhere, but `Context()` raises `MSMError` unless the
+CUDA library is present and a device is visible.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+DEFAULT_LIB = os.path.join(os.path.dirname(_PKG), "lib", "libg16cuda.so")
+
+G16_OK, G16_ERR_INVALID, G16_ERR_CUDA, G16_ERR_NO_DEVICE, G16_ERR_OOM, G16_ERR_LENGTH = range(6)
+G1_WORDS64, G2_WORDS64 = 12, 24
+G1_PARTIAL_WORDS, G2_PARTIAL_WORDS = 48, 96
+G1_AFFINE_WORDS, G2_AFFINE_WORDS = 25, 49
+
+EXPORTS = [
+    "g16_version", "g16_device_count", "g16_ctx_create", "g16_ctx_destroy", "g16_last_error",
+    "g16_ctx_set_stream", "g16_ctx_synchronize", "g16_ctx_set_window_bits",
+    "g16_g1_bases_upload", "g16_g2_bases_upload", "g16_g1_bases_from_device", "g16_g2_bases_from_device",
+    "g16_bases_free", "g16_bases_len",
+    "g16_g1_msm", "g16_g2_msm", "g16_g1_msm_oneshot", "g16_g2_msm_oneshot",
+    "g16_g1_msm_device", "g16_g2_msm_device",
+    "g16_g1_combine_partials_device", "g16_g2_combine_partials_device",
+    "g16_g1_fixed_base_mul", "g16_g2_fixed_base_mul",
+    "g16_g1_fixed_base_mul_device", "g16_g2_fixed_base_mul_device",
+    "g16_pk_upload", "g16_pk_free", "g16_prove",
+]
+
+
+class MSMError(RuntimeError):
+    """Counterpart of GrothError::MSMError(String) (crates/groth16-core/src/lib.rs:74-76)."""
+
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"MSM computation error: {msg} (code {code})")
+        self.code = code
+
+
+class _PkHost(ctypes.Structure):
+    _fields_ = [
+        ("alpha_g1", ctypes.c_void_p), ("beta_g1", ctypes.c_void_p), ("delta_g1", ctypes.c_void_p),
+        ("beta_g2", ctypes.c_void_p), ("delta_g2", ctypes.c_void_p),
+        ("a_g1", ctypes.c_void_p), ("a_g1_inf", ctypes.c_void_p), ("a_len", ctypes.c_size_t),
+        ("b_g1", ctypes.c_void_p), ("b_g1_inf", ctypes.c_void_p), ("b1_len", ctypes.c_size_t),
+        ("b_g2", ctypes.c_void_p), ("b_g2_inf", ctypes.c_void_p), ("b2_len", ctypes.c_size_t),
+        ("ic_g1", ctypes.c_void_p), ("ic_g1_inf", ctypes.c_void_p), ("ic_len", ctypes.c_size_t),
+        ("h_g1", ctypes.c_void_p), ("h_g1_inf", ctypes.c_void_p), ("h_len", ctypes.c_size_t),
+        ("num_public", ctypes.c_size_t),
+    ]
+
+
+_libs = {}
+
+
+def load_library(path: Optional[str] = None) -> ctypes.CDLL:
+    path = path or DEFAULT_LIB
+    if path in _libs:
+        return _libs[path]
+    if not os.path.exists(path):
+        raise MSMError(G16_ERR_NO_DEVICE, f"{path} not found: build it with `python zero-knowledge-proofs_b200/build.py` "
+                                          "(there is no CPU fallback)")
+    lib = ctypes.CDLL(path)
+    vp, sz, ci = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int
+    lib.g16_version.restype = ctypes.c_char_p
+    lib.g16_last_error.restype = ctypes.c_char_p
+    lib.g16_last_error.argtypes = [vp]
+    lib.g16_device_count.restype = ci
+    lib.g16_ctx_create.argtypes = [vp, ci, ctypes.POINTER(vp)]
+    lib.g16_ctx_destroy.argtypes = [vp]
+    lib.g16_ctx_destroy.restype = None
+    lib.g16_ctx_set_stream.argtypes = [vp, vp]
+    lib.g16_ctx_synchronize.argtypes = [vp]
+    lib.g16_ctx_set_window_bits.argtypes = [vp, ctypes.c_uint]
+    for g in ("g1", "g2"):
+        getattr(lib, f"g16_{g}_bases_upload").argtypes = [vp, vp, vp, sz, ctypes.POINTER(vp)]
+        getattr(lib, f"g16_{g}_bases_from_device").argtypes = [vp, vp, sz, ctypes.POINTER(vp)]
+        getattr(lib, f"g16_{g}_msm").argtypes = [vp, vp, vp, sz, vp, vp]
+        getattr(lib, f"g16_{g}_msm_oneshot").argtypes = [vp, vp, vp, vp, sz, vp, vp]
+        getattr(lib, f"g16_{g}_msm_device").argtypes = [vp, vp, vp, sz, vp, vp]
+        getattr(lib, f"g16_{g}_combine_partials_device").argtypes = [vp, vp, sz, vp]
+        getattr(lib, f"g16_{g}_fixed_base_mul").argtypes = [vp, vp, vp, sz, vp, vp]
+        getattr(lib, f"g16_{g}_fixed_base_mul_device").argtypes = [vp, vp, vp, sz, vp]
+    lib.g16_bases_free.argtypes = [vp]
+    lib.g16_bases_free.restype = None
+    lib.g16_bases_len.argtypes = [vp]
+    lib.g16_bases_len.restype = sz
+    lib.g16_pk_upload.argtypes = [vp, ctypes.POINTER(_PkHost), ctypes.POINTER(vp)]
+    lib.g16_pk_free.argtypes = [vp]
+    lib.g16_pk_free.restype = None
+    lib.g16_prove.argtypes = [vp, vp, vp, sz, vp, sz, vp, vp, vp, vp, vp, vp, vp, vp]
+    _libs[path] = lib
+    return lib
+
+
+def _u64(a, width=None) -> np.ndarray:
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    if width is not None:
+        a = a.reshape(-1, width)
+    return a
+
+
+def _ptr(a) -> Optional[int]:
+    return None if a is None else a.ctypes.data
+
+
+class Bases:
+    """Device-resident base points (g16_bases)."""
+
+    def __init__(self, ctx: "Context", handle: int, group: int, keepalive=None):
+        self.ctx, self.handle, self.group, self._keep = ctx, handle, group, keepalive
+
+    def __len__(self):
+        return int(self.ctx.lib.g16_bases_len(self.handle))
+
+    def free(self):
+        if self.handle:
+            self.ctx.lib.g16_bases_free(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class ProvingKeyDevice:
+    def __init__(self, ctx: "Context", handle: int):
+        self.ctx, self.handle = ctx, handle
+
+    def free(self):
+        if self.handle:
+            self.ctx.lib.g16_pk_free(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Context:
+    def __init__(self, devices: Optional[Sequence[int]] = None, lib_path: Optional[str] = None):
+        self.lib = load_library(lib_path)
+        h = ctypes.c_void_p()
+        if devices:
+            arr = (ctypes.c_int * len(devices))(*devices)
+            rc = self.lib.g16_ctx_create(arr, len(devices), ctypes.byref(h))
+        else:
+            rc = self.lib.g16_ctx_create(None, 0, ctypes.byref(h))
+        if rc != G16_OK:
+            raise MSMError(rc, self.lib.g16_last_error(None).decode())
+        self.handle = h.value
+
+    # ---- plumbing
+    def _check(self, rc: int):
+        if rc != G16_OK:
+            raise MSMError(rc, self.lib.g16_last_error(self.handle).decode())
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.g16_ctx_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream: int):
+        self._check(self.lib.g16_ctx_set_stream(self.handle, cuda_stream))
+
+    def synchronize(self):
+        self._check(self.lib.g16_ctx_synchronize(self.handle))
+
+    def set_window_bits(self, c: int):
+        self._check(self.lib.g16_ctx_set_window_bits(self.handle, c))
+
+    # ---- bases
+    def _upload(self, g: str, xy, inf) -> Bases:
+        width = G1_WORDS64 if g == "g1" else G2_WORDS64
+        xy = _u64(xy, width)
+        n = xy.shape[0]
+        if inf is not None:
+            inf = np.ascontiguousarray(inf, dtype=np.uint8)
+            if inf.shape[0] != n:
+                raise MSMError(G16_ERR_LENGTH, "infinity flags length mismatch")
+        h = ctypes.c_void_p()
+        self._check(getattr(self.lib, f"g16_{g}_bases_upload")(self.handle, _ptr(xy), _ptr(inf), n, ctypes.byref(h)))
+        return Bases(self, h.value, 1 if g == "g1" else 2)
+
+    def g1_bases_upload(self, xy, inf=None) -> Bases:
+        return self._upload("g1", xy, inf)
+
+    def g2_bases_upload(self, xy, inf=None) -> Bases:
+        return self._upload("g2", xy, inf)
+
+    def bases_from_device(self, g: str, dev_ptr: int, n: int, keepalive=None) -> Bases:
+        h = ctypes.c_void_p()
+        self._check(getattr(self.lib, f"g16_{g}_bases_from_device")(self.handle, dev_ptr, n, ctypes.byref(h)))
+        return Bases(self, h.value, 1 if g == "g1" else 2, keepalive)
+
+    # ---- MSM with resident bases
+    def _msm(self, g: str, bases: Bases, scalars) -> Tuple[np.ndarray, int]:
+        width = G1_WORDS64 if g == "g1" else G2_WORDS64
+        scalars = _u64(scalars, 4)
+        out = np.zeros(width, dtype=np.uint64)
+        inf = np.zeros(1, dtype=np.uint8)
+        self._check(getattr(self.lib, f"g16_{g}_msm")(self.handle, bases.handle, _ptr(scalars), scalars.shape[0],
+                                                     _ptr(out), _ptr(inf)))
+        return out, int(inf[0])
+
+    def g1_msm(self, bases: Bases, scalars):
+        return self._msm("g1", bases, scalars)
+
+    def g2_msm(self, bases: Bases, scalars):
+        return self._msm("g2", bases, scalars)
+
+    # ---- the reference seam: fresh (scalar, point) lists per call
+    def _oneshot(self, g: str, xy, inf, scalars):
+        width = G1_WORDS64 if g == "g1" else G2_WORDS64
+        xy = _u64(xy, width)
+        scalars = _u64(scalars, 4)
+        if xy.shape[0] != scalars.shape[0]:
+            # ark: `msm` returns Err(min_len) -> GrothError::MSMError (lib.rs:283,297)
+            raise MSMError(G16_ERR_LENGTH, f"G{1 if g == 'g1' else 2} MSM failed: {min(xy.shape[0], scalars.shape[0])}")
+        if inf is not None:
+            inf = np.ascontiguousarray(inf, dtype=np.uint8)
+        out = np.zeros(width, dtype=np.uint64)
+        oinf = np.zeros(1, dtype=np.uint8)
+        self._check(getattr(self.lib, f"g16_{g}_msm_oneshot")(self.handle, _ptr(xy), _ptr(inf), _ptr(scalars),
+                                                             xy.shape[0], _ptr(out), _ptr(oinf)))
+        return out, int(oinf[0])
+
+    def multi_scalar_mult_g1(self, scalars, points_xy, points_inf=None):
+        """Prover::multi_scalar_mult_g1: sum s_i P_i as an affine point; empty input -> identity."""
+        return self._oneshot("g1", points_xy, points_inf, scalars)
+
+    def multi_scalar_mult_g2(self, scalars, points_xy, points_inf=None):
+        return self._oneshot("g2", points_xy, points_inf, scalars)
+
+    # ---- device-resident variants (pointers are plain ints, e.g. torch.Tensor.data_ptr())
+    def msm_device(self, g: str, bases: Bases, dev_scalars: int, n: int, dev_out_affine: int = 0, dev_out_partial: int = 0):
+        self._check(getattr(self.lib, f"g16_{g}_msm_device")(self.handle, bases.handle, dev_scalars, n,
+                                                            dev_out_affine or None, dev_out_partial or None))
+
+    def combine_partials_device(self, g: str, dev_partials: int, k: int, dev_out_affine: int):
+        self._check(getattr(self.lib, f"g16_{g}_combine_partials_device")(self.handle, dev_partials, k, dev_out_affine))
+
+    # ---- fixed base
+    def _fixed(self, g: str, base_xy, scalars):
+        width = G1_WORDS64 if g == "g1" else G2_WORDS64
+        base_xy = _u64(base_xy).reshape(width)
+        scalars = _u64(scalars, 4)
+        n = scalars.shape[0]
+        out = np.zeros((n, width), dtype=np.uint64)
+        inf = np.zeros(n, dtype=np.uint8)
+        self._check(getattr(self.lib, f"g16_{g}_fixed_base_mul")(self.handle, _ptr(base_xy), _ptr(scalars), n,
+                                                                _ptr(out), _ptr(inf)))
+        return out, inf
+
+    def fixed_base_mul_g1(self, base_xy, scalars):
+        """[(base * s).into_affine() for s in scalars] (crates/groth16-setup/src/lib.rs:185-241)."""
+        return self._fixed("g1", base_xy, scalars)
+
+    def fixed_base_mul_g2(self, base_xy, scalars):
+        return self._fixed("g2", base_xy, scalars)
+
+    def fixed_base_mul_device(self, g: str, base_xy, dev_scalars: int, n: int, dev_out: int):
+        width = G1_WORDS64 if g == "g1" else G2_WORDS64
+        base_xy = _u64(base_xy).reshape(width)
+        self._check(getattr(self.lib, f"g16_{g}_fixed_base_mul_device")(self.handle, _ptr(base_xy), dev_scalars, n, dev_out))
+
+    # ---- prove
+    def pk_upload(self, pk: dict) -> ProvingKeyDevice:
+        """pk: dict with alpha_g1, beta_g1, delta_g1 (12 u64), beta_g2, delta_g2 (24 u64), a_g1, b_g1, ic_g1, h_g1
+        (n x 12), b_g2 (n x 24), optional *_inf byte arrays, num_public."""
+        keep = []
+
+        def arr(name, width):
+            a = _u64(pk[name], width)
+            keep.append(a)
+            return a
+
+        def flags(name, n):
+            f = pk.get(name + "_inf")
+            if f is None:
+                return None
+            f = np.ascontiguousarray(f, dtype=np.uint8)
+            assert f.shape[0] == n
+            keep.append(f)
+            return f
+
+        s = _PkHost()
+        for name, width in (("alpha_g1", 12), ("beta_g1", 12), ("delta_g1", 12), ("beta_g2", 24), ("delta_g2", 24)):
+            setattr(s, name, _ptr(arr(name, width)))
+        for name, width, ln in (("a_g1", 12, "a_len"), ("b_g1", 12, "b1_len"), ("b_g2", 24, "b2_len"),
+                                ("ic_g1", 12, "ic_len"), ("h_g1", 12, "h_len")):
+            a = arr(name, width)
+            setattr(s, name, _ptr(a) if a.shape[0] else None)
+            setattr(s, name + "_inf", _ptr(flags(name, a.shape[0])))
+            setattr(s, ln, a.shape[0])
+        s.num_public = int(pk["num_public"])
+        h = ctypes.c_void_p()
+        self._check(self.lib.g16_pk_upload(self.handle, ctypes.byref(s), ctypes.byref(h)))
+        return ProvingKeyDevice(self, h.value)
+
+    def prove(self, pk: ProvingKeyDevice, assignment_fr, h_coeffs, r, s):
+        """Group part of Prover::prove.  Returns ((a_xy, a_inf), (b_xy, b_inf), (c_xy, c_inf))."""
+        assignment_fr = _u64(assignment_fr, 4)
+        h_coeffs = _u64(h_coeffs if h_coeffs is not None else np.zeros((0, 4)), 4)
+        r = _u64(r).reshape(4)
+        s = _u64(s).reshape(4)
+        a = np.zeros(12, dtype=np.uint64); b = np.zeros(24, dtype=np.uint64); c = np.zeros(12, dtype=np.uint64)
+        fl = np.zeros(3, dtype=np.uint8)
+        self._check(self.lib.g16_prove(self.handle, pk.handle, _ptr(assignment_fr), assignment_fr.shape[0],
+                                       _ptr(h_coeffs) if h_coeffs.shape[0] else None, h_coeffs.shape[0],
+                                       _ptr(r), _ptr(s), _ptr(a), fl.ctypes.data, _ptr(b), fl.ctypes.data + 1,
+                                       _ptr(c), fl.ctypes.data + 2))
+        return (a, int(fl[0])), (b, int(fl[1])), (c, int(fl[2]))
