@@ -133,6 +133,25 @@ int g16_prove(g16_ctx *ctx, const g16_pk *pk, const uint64_t *assignment_fr, siz
               const uint64_t *h_coeffs, size_t num_h, const uint64_t r[4], const uint64_t s[4],
               uint64_t a_xy[12], uint8_t *a_inf, uint64_t b_xy[24], uint8_t *b_inf, uint64_t c_xy[12], uint8_t *c_inf);
 
+/* ---- test hooks (used by tests/ and bench.py only) ------------------------------------------ */
+/* kernels launched by the library since it was loaded */
+unsigned long long g16_launch_count(void);
+/* CUDA-event timing of the stages of the last MSM on a single-device ctx, in ms:
+ * [digit count, offset scan, scatter, bucket accumulate, bucket reduce, window combine];
+ * plan = {window bits, windows, buckets per window} */
+int g16_ctx_enable_stage_timing(g16_ctx *ctx, int on);
+int g16_ctx_last_stage_ms(g16_ctx *ctx, float ms[6], unsigned plan[3]);
+/* element-wise Fq ops on the device: op 0 mul, 1 add, 2 sub, 3 inverse(a), 4 square(a), 5 negate(a);
+ * a, b, out: n x 6 u64 Montgomery (b may be NULL for unary ops) */
+int g16_debug_fq_op(g16_ctx *ctx, int op, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n);
+/* Fr Montgomery -> canonical (`into_bigint()`), n x 4 u64 */
+int g16_debug_fr_from_mont(g16_ctx *ctx, const uint64_t *a, uint64_t *out, size_t n);
+/* out[i] = affine(P[i] + Q[i]) through the XYZZ mixed addition, all exceptional cases included */
+int g16_debug_g1_add(g16_ctx *ctx, const uint64_t *p, const uint8_t *p_inf, const uint64_t *q, const uint8_t *q_inf,
+                     uint64_t *out_xy, uint8_t *out_inf, size_t n);
+int g16_debug_g2_add(g16_ctx *ctx, const uint64_t *p, const uint8_t *p_inf, const uint64_t *q, const uint8_t *q_inf,
+                     uint64_t *out_xy, uint8_t *out_inf, size_t n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,32 @@
+"""CPU-side (no GPU) check of the engine's pipeline logic: the kernel bodies of
+zero-knowledge-proofs_b200/csrc are compiled for the host by tests/emu/build_emu.py and driven through
+the same C ABI.  This validates digit decomposition, the counting sort, bucket accumulation with all
+exceptional group cases, the multi-level bucket reduction, the window fold and the fixed-base tables
+before any GPU time is spent.  The emulation library is test infrastructure; the product never loads it."""
+import parity_cases as pc
+
+
+def test_emu_golden_msm(emu_ctx):
+    pc.check_golden_msm(emu_ctx)
+    pc.check_empty(emu_ctx)
+    pc.check_length_mismatch(emu_ctx)
+
+
+def test_emu_golden_fixed_base(emu_ctx, gens):
+    pc.check_golden_fixed_base(emu_ctx, gens)
+
+
+def test_emu_field_and_group_hooks(emu_ctx, oracle, gens):
+    pc.check_debug_field(emu_ctx, oracle, n=300)
+    pc.check_debug_group_add(emu_ctx, oracle, gens)
+
+
+def test_emu_random_and_window_sweep(emu_ctx, oracle, gens):
+    pc.check_random_msm(emu_ctx, oracle, gens, "g1", 257, 1, windows=(0, 2, 3, 7, 11, 16))
+    pc.check_random_msm(emu_ctx, oracle, gens, "g2", 40, 2, windows=(0, 5))
+
+
+def test_emu_adversarial_and_skewed(emu_ctx, oracle, gens):
+    pc.check_adversarial(emu_ctx, oracle, gens, "g1", 300, 5)
+    pc.check_adversarial(emu_ctx, oracle, gens, "g2", 60, 6)
+    pc.check_skewed_scalars(emu_ctx, oracle, gens, 200, 7)

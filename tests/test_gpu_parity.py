@@ -1,0 +1,164 @@
+"""Parity tests proper (`-m gpu`): the CUDA engine, called through the C ABI, against the CPU oracle
+on identical inputs -- bit-exact, as SURVEY.md 8 requires for integer work."""
+import os
+
+import numpy as np
+import pytest
+
+import helpers
+import parity_cases as pc
+
+pytestmark = pytest.mark.gpu
+
+
+def test_library_is_the_cuda_build(gpu_ctx):
+    import groth16_cuda
+    assert os.path.samefile(groth16_cuda.DEFAULT_LIB, gpu_ctx.lib._name)
+    assert b"sm_100a" in gpu_ctx.lib.g16_version()
+    assert gpu_ctx.lib.g16_device_count() >= 1
+
+
+def test_field_ops_on_device(gpu_ctx, oracle):
+    pc.check_debug_field(gpu_ctx, oracle, n=200000)
+
+
+def test_group_add_exceptional_cases(gpu_ctx, oracle, gens):
+    pc.check_debug_group_add(gpu_ctx, oracle, gens)
+
+
+def test_golden_msm(gpu_ctx):
+    pc.check_golden_msm(gpu_ctx)
+    pc.check_empty(gpu_ctx)
+    pc.check_length_mismatch(gpu_ctx)
+
+
+def test_golden_fixed_base(gpu_ctx, gens):
+    pc.check_golden_fixed_base(gpu_ctx, gens)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 31, 32, 33, 1000])
+def test_g1_small_sizes(gpu_ctx, oracle, gens, n):
+    pc.check_random_msm(gpu_ctx, oracle, gens, "g1", n, n)
+
+
+def test_g1_window_sweep(gpu_ctx, oracle, gens):
+    pc.check_random_msm(gpu_ctx, oracle, gens, "g1", 3000, 3, windows=(0, 2, 3, 5, 8, 11, 13, 16, 20))
+
+
+def test_g1_2_16_config2(gpu_ctx, oracle, gens):
+    """BASELINE config 2: standalone G1 MSM, 2^16 random scalars/points."""
+    pc.check_random_msm(gpu_ctx, oracle, gens, "g1", 1 << 16, 16)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 40, 1 << 12])
+def test_g2_sizes(gpu_ctx, oracle, gens, n):
+    pc.check_random_msm(gpu_ctx, oracle, gens, "g2", n, 100 + n, windows=(0, 7) if n == 40 else (0,))
+
+
+def test_adversarial_sets(gpu_ctx, oracle, gens):
+    pc.check_adversarial(gpu_ctx, oracle, gens, "g1", 1 << 13, 5)
+    pc.check_adversarial(gpu_ctx, oracle, gens, "g2", 1 << 10, 6)
+
+
+def test_reference_faithful_scalar_distributions(gpu_ctx, oracle, gens):
+    pc.check_skewed_scalars(gpu_ctx, oracle, gens, 1 << 13, 7)
+
+
+def test_fixed_base(gpu_ctx, oracle, gens):
+    pc.check_fixed_base_random(gpu_ctx, oracle, gens, 1 << 12, 9)
+
+
+def test_device_resident_path_and_partials(gpu_ctx, oracle, gens):
+    """Index-range shards -> projective partials -> combine == one-shot result (the multi-GPU data path,
+    exercised on one device)."""
+    import torch
+    n, shards = 6000, 3
+    pts, inf = helpers.make_points(oracle, gens, "g1", 0xabc, n)
+    sc = oracle.gen_scalars(0xdef, n)
+    exp, einf = oracle.g1_msm(pts, inf, sc, threads=oracle.max_threads())
+    dev = torch.device("cuda:0")
+    gpu_ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    d_sc = torch.from_numpy(sc.view(np.int64)).to(dev)
+    partials = torch.zeros((shards, 48), dtype=torch.int32, device=dev)
+    keep = []
+    for k in range(shards):
+        lo, hi = n * k // shards, n * (k + 1) // shards
+        b = gpu_ctx.g1_bases_upload(pts[lo:hi], inf[lo:hi])
+        keep.append(b)
+        gpu_ctx.msm_device("g1", b, d_sc[lo:hi].data_ptr(), hi - lo, 0, partials[k].data_ptr())
+    out = torch.zeros(25, dtype=torch.int32, device=dev)
+    gpu_ctx.combine_partials_device("g1", partials.data_ptr(), shards, out.data_ptr())
+    torch.cuda.synchronize()
+    host = out.cpu().numpy().view(np.uint32)
+    assert int(host[24]) == einf
+    assert (host[:24].view(np.uint64) == exp).all()
+
+
+def test_multi_device_context_matches_single(gpu_ctx, oracle, gens):
+    import groth16_cuda
+    ndev = gpu_ctx.lib.g16_device_count()
+    devs = list(range(min(ndev, 8)))
+    if len(devs) < 2:
+        devs = [0, 0]          # two shards on one device: same host-side sharding/combination code
+    ctx = groth16_cuda.Context(devices=devs)
+    try:
+        pc.check_random_msm(ctx, oracle, gens, "g1", 5000, 41)
+        pc.check_random_msm(ctx, oracle, gens, "g2", 300, 42)
+        pc.check_fixed_base_random(ctx, oracle, gens, 512, 43)
+    finally:
+        ctx.close()
+
+
+def _dot_mod_r(a_mont, b_mont, oracle):
+    import bls12_381 as bls
+    a = oracle.fr_from_mont(a_mont); b = oracle.fr_from_mont(b_mont)
+    acc = 0
+    w = [1 << (64 * i) for i in range(4)]
+    for i in range(a.shape[0]):
+        x = int(a[i, 0]) + int(a[i, 1]) * w[1] + int(a[i, 2]) * w[2] + int(a[i, 3]) * w[3]
+        y = int(b[i, 0]) + int(b[i, 1]) * w[1] + int(b[i, 2]) * w[2] + int(b[i, 3]) * w[3]
+        acc += x * y
+    return acc % bls.R
+
+
+@pytest.mark.parametrize("log_n", [20])
+def test_large_msm_by_discrete_log(gpu_ctx, oracle, gens, log_n):
+    """Size-independent exact check at sizes the CPU oracle cannot reach in seconds: with bases
+    P_i = k_i G (built on the GPU by the fixed-base kernel), sum s_i P_i must equal (sum s_i k_i mod r) G,
+    which the oracle computes with one scalar multiplication."""
+    import bls12_381 as bls
+    import torch
+    n = 1 << log_n
+    dev = torch.device("cuda:0")
+    gpu_ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    k = oracle.gen_scalars(0xba5e0000 + log_n, n)
+    s = oracle.gen_scalars(0x5eed0000 + log_n, n)
+    d_k = torch.from_numpy(k.view(np.int64)).to(dev)
+    d_s = torch.from_numpy(s.view(np.int64)).to(dev)
+    d_pts = torch.empty((n, 24), dtype=torch.int32, device=dev)
+    gpu_ctx.fixed_base_mul_device("g1", gens[0], d_k.data_ptr(), n, d_pts.data_ptr())
+    # spot-check the generated bases against the oracle
+    torch.cuda.synchronize()
+    idx = [0, 1, n // 2, n - 1]
+    got = d_pts[idx].cpu().numpy().view(np.uint32).view(np.uint64)
+    exp, _ = oracle.g1_fixed_base_mul(gens[0], k[idx])
+    assert (got == exp).all()
+    bases = gpu_ctx.bases_from_device("g1", d_pts.data_ptr(), n, keepalive=d_pts)
+    out = torch.zeros(25, dtype=torch.int32, device=dev)
+    gpu_ctx.msm_device("g1", bases, d_s.data_ptr(), n, out.data_ptr(), 0)
+    torch.cuda.synchronize()
+    host = out.cpu().numpy().view(np.uint32)
+    e = _dot_mod_r(s, k, oracle)
+    exp, einf = oracle.g1_fixed_base_mul(gens[0], np.array([bls.fr_to_mont(e)], dtype=np.uint64))
+    assert int(host[24]) == int(einf[0])
+    assert (host[:24].view(np.uint64) == exp[0]).all()
+    # linearity: msm(s + s', P) == msm(s, P) + msm(s', P), checked through the same identity
+    s2 = oracle.gen_scalars(0x77 + log_n, n)
+    d_s2 = torch.from_numpy(s2.view(np.int64)).to(dev)
+    gpu_ctx.msm_device("g1", bases, d_s2.data_ptr(), n, out.data_ptr(), 0)
+    torch.cuda.synchronize()
+    host2 = out.cpu().numpy().view(np.uint32)
+    e2 = _dot_mod_r(s2, k, oracle)
+    exp2, _ = oracle.g1_fixed_base_mul(gens[0], np.array([bls.fr_to_mont(e2)], dtype=np.uint64))
+    assert (host2[:24].view(np.uint64) == exp2[0]).all()
+    bases.free()

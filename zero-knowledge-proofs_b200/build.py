@@ -67,7 +67,17 @@ def build(force: bool = False, jobs: int | None = None, verbose: bool = False) -
     for unit, dt, what in results:
         if what == "built":
             print(f"[build] {unit}: {dt:.1f}s")
+    build_tools(force)
     return LIB
+
+
+def build_tools(force: bool = False) -> str:
+    """lib/imad_peak: the integer-pipe roofline microbenchmark bench.py runs before the timed region."""
+    src = os.path.join(HERE, "tools", "imad_peak.cu")
+    out = os.path.join(LIBDIR, "imad_peak")
+    if force or not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(src), _newest_header()):
+        subprocess.run([NVCC] + ARCH + ["-O3", "-std=c++17", "-lineinfo", "-o", out, src], check=True)
+    return out
 
 
 if __name__ == "__main__":

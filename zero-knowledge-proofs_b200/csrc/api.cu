@@ -108,6 +108,7 @@ void g16_ctx_destroy(g16_ctx *ctx) {
         if (d.stream) cudaStreamSynchronize(d.stream);
 #endif
         d.ws.release();
+        d.timer.destroy();
 #ifndef G16_EMU
         if (d.own_stream && d.stream) cudaStreamDestroy(d.stream);
 #endif
@@ -432,6 +433,85 @@ int g16_prove(g16_ctx *ctx, const g16_pk *pk, const uint64_t *assignment_fr, siz
         if (b_inf) *b_inf = inf_b;
         if (c_inf) *c_inf = inf_c;
     });
+}
+
+// ---- test hooks --------------------------------------------------------------------------------
+unsigned long long g16_launch_count(void) { return launch_count(); }
+
+int g16_ctx_enable_stage_timing(g16_ctx *ctx, int on) {
+    if (!ctx) return G16_ERR_INVALID;
+    for (auto &d : ctx->c.devs) { d.timer.enabled = on != 0; d.timer.valid = false; }
+    return G16_OK;
+}
+int g16_ctx_last_stage_ms(g16_ctx *ctx, float ms[6], unsigned plan[3]) {
+    if (!ctx) return G16_ERR_INVALID;
+    return guarded(ctx, [&] {
+        Device &dv = single_device(ctx);
+        stream_sync(dv.stream);
+        require(dv.timer.read(ms), "no timed MSM has run (g16_ctx_enable_stage_timing)");
+        if (plan) { plan[0] = dv.last_plan.c; plan[1] = dv.last_plan.nwin; plan[2] = dv.last_plan.nb; }
+    });
+}
+
+int g16_debug_fq_op(g16_ctx *ctx, int op, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n) {
+    if (!ctx) return G16_ERR_INVALID;
+    return guarded(ctx, [&] {
+        Device &dv = single_device(ctx);
+        require(a && out, "NULL argument");
+        uint32_t *d = dv.ws.staging.as<uint32_t>(n * 36 + 36);
+        copy_h2d(d, a, n * 48, dv.stream);
+        if (b) copy_h2d(d + n * 12, b, n * 48, dv.stream);
+        k_debug_fq_op(dv.stream, n, op, d, b ? d + n * 12 : nullptr, d + n * 24);
+        copy_d2h(out, d + n * 24, n * 48, dv.stream);
+        stream_sync(dv.stream);
+    });
+}
+int g16_debug_fr_from_mont(g16_ctx *ctx, const uint64_t *a, uint64_t *out, size_t n) {
+    if (!ctx) return G16_ERR_INVALID;
+    return guarded(ctx, [&] {
+        Device &dv = single_device(ctx);
+        require(a && out, "NULL argument");
+        uint32_t *d = dv.ws.staging.as<uint32_t>(n * 16 + 16);
+        copy_h2d(d, a, n * 32, dv.stream);
+        k_debug_fr_from_mont(dv.stream, n, d, d + n * 8);
+        copy_d2h(out, d + n * 8, n * 32, dv.stream);
+        stream_sync(dv.stream);
+    });
+}
+extern "C++" {
+template <class F>
+static int debug_add_impl(g16_ctx *ctx, const uint64_t *p, const uint8_t *p_inf, const uint64_t *q, const uint8_t *q_inf,
+                          uint64_t *out_xy, uint8_t *out_inf, size_t n) {
+    if (!ctx) return G16_ERR_INVALID;
+    return guarded(ctx, [&] {
+        Device &dv = single_device(ctx);
+        require(p && q && out_xy, "NULL argument");
+        constexpr size_t W = 2 * FieldWords<F>::N;
+        uint32_t *dp = import_points<F>(dv, p, p_inf, n);
+        uint32_t *dq = nullptr;
+        try {
+            dq = import_points<F>(dv, q, q_inf, n);
+            uint32_t *d_out = dv.ws.fb_out.as<uint32_t>(n * W);
+            k_debug_add<F>(dv.stream, n, dp, dq, d_out);
+            copy_d2h(out_xy, d_out, n * W * 4, dv.stream);
+            if (out_inf) {
+                uint8_t *d_fl = dv.ws.fb_flags.as<uint8_t>(n);
+                k_export_flags<F>(dv.stream, n, d_out, d_fl);
+                copy_d2h(out_inf, d_fl, n, dv.stream);
+            }
+            stream_sync(dv.stream);
+        } catch (...) { dev_free(dp); dev_free(dq); throw; }
+        dev_free(dp); dev_free(dq);
+    });
+}
+}  // extern "C++"
+int g16_debug_g1_add(g16_ctx *ctx, const uint64_t *p, const uint8_t *p_inf, const uint64_t *q, const uint8_t *q_inf,
+                     uint64_t *out_xy, uint8_t *out_inf, size_t n) {
+    return debug_add_impl<Fq>(ctx, p, p_inf, q, q_inf, out_xy, out_inf, n);
+}
+int g16_debug_g2_add(g16_ctx *ctx, const uint64_t *p, const uint8_t *p_inf, const uint64_t *q, const uint8_t *q_inf,
+                     uint64_t *out_xy, uint8_t *out_inf, size_t n) {
+    return debug_add_impl<Fq2>(ctx, p, p_inf, q, q_inf, out_xy, out_inf, n);
 }
 
 }  // extern "C"

@@ -25,11 +25,54 @@ struct Workspace {
     }
 };
 
+// optional per-stage CUDA-event timing of the last MSM on a device (bench.py reads it to put the
+// dominant kernel's measured duration into the roofline line)
+constexpr int N_STAGES = 6;  // count, scan, scatter, accumulate, reduce, combine
+struct StageTimer {
+    bool enabled = false;
+#ifndef G16_EMU
+    cudaEvent_t ev[N_STAGES + 1] = {};
+    bool created = false;
+#endif
+    bool valid = false;
+    void mark(int i, stream_t s) {
+#ifndef G16_EMU
+        if (!enabled) return;
+        if (!created) {
+            for (auto &e : ev) G16_CUDA_CHECK(cudaEventCreate(&e));
+            created = true;
+        }
+        G16_CUDA_CHECK(cudaEventRecord(ev[i], s));
+        if (i == N_STAGES) valid = true;
+#else
+        (void)i; (void)s;
+#endif
+    }
+    // call after the stream has been synchronised
+    bool read(float *ms) {
+#ifndef G16_EMU
+        if (!enabled || !valid) return false;
+        for (int i = 0; i < N_STAGES; ++i) G16_CUDA_CHECK(cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]));
+        return true;
+#else
+        (void)ms; return false;
+#endif
+    }
+    void destroy() {
+#ifndef G16_EMU
+        if (created) for (auto &e : ev) cudaEventDestroy(e);
+        created = false;
+#endif
+    }
+};
+
 struct Device {
     int id = 0;
     stream_t stream = nullptr;
     bool own_stream = false;
     Workspace ws;
+    StageTimer timer;
+    MsmPlan last_plan{};
 };
 
 inline void set_device(int id) {
@@ -110,22 +153,28 @@ void msm_run(Device &dv, const uint32_t *pts, const uint32_t *d_scalars, size_t 
     size_t total = plan.total;
     if ((double)n * plan.nwin >= 4294967295.0) throw Error{G16_ERR_INVALID, "n * windows exceeds 2^32 entries"};
 
+    dv.last_plan = plan;
+    dv.timer.mark(0, s);
     // 1. bucket sizes
     uint32_t *counts = ws.counts.as<uint32_t>(total + 1);
     dev_memset(counts, 0, (total + 1) * sizeof(uint32_t), s);
     k_digit_count(s, n, d_scalars, mont, plan, counts);
+    dv.timer.mark(1, s);
     // 2. bucket offsets (exclusive scan; offsets[total] = number of entries)
     uint32_t *scan_tmp = ws.scan_tmp.as<uint32_t>(k_scan_tmp_words(total + 1));
     k_exclusive_scan(s, counts, counts, total + 1, scan_tmp);
     uint32_t *offsets = counts;
+    dv.timer.mark(2, s);
     // 3. scatter (point index, sign) into bucket order
     uint32_t *cursor = ws.cursor.as<uint32_t>(total);
     copy_d2d(cursor, offsets, total * sizeof(uint32_t), s);
     uint32_t *entries = ws.entries.as<uint32_t>(n * plan.nwin);
     k_digit_scatter(s, n, d_scalars, mont, plan, cursor, entries);
+    dv.timer.mark(3, s);
     // 4. bucket accumulation (the hot kernel)
     uint32_t *buckets = ws.buckets.as<uint32_t>(total * 4 * FieldWords<F>::N);
     k_accumulate<F>(s, total, pts, entries, offsets, buckets);
+    dv.timer.mark(4, s);
     // 5. parallel bucket reduction
     const uint32_t *X = buckets, *Y = nullptr;
     uint32_t n_in = plan.nb, level = 0;
@@ -138,8 +187,10 @@ void msm_run(Device &dv, const uint32_t *pts, const uint32_t *d_scalars, size_t 
         X = Xo; Y = Yo;
         n_in = n_out; ++level; flip ^= 2;
     }
+    dv.timer.mark(5, s);
     // 6. window fold + to affine
     k_window_combine<F>(s, X, Y, plan.nwin, plan.c, d_out_xyzz, d_out_aff);
+    dv.timer.mark(6, s);
 }
 
 // Import host points (ark layout + infinity bytes) into a device shard.

@@ -56,4 +56,11 @@ void k_fb_table(stream_t s, const uint32_t *powers, uint32_t *table);
 template <class F>
 void k_fb_mul(stream_t s, size_t n, const uint32_t *scalars, bool mont, const uint32_t *table, uint32_t *out);
 
+// test hooks
+void k_debug_fq_op(stream_t s, size_t n, int op, const uint32_t *a, const uint32_t *b, uint32_t *out);
+void k_debug_fr_from_mont(stream_t s, size_t n, const uint32_t *a, uint32_t *out);
+template <class F>
+void k_debug_add(stream_t s, size_t n, const uint32_t *p, const uint32_t *q, uint32_t *out);
+unsigned long long launch_count();
+
 }  // namespace g16

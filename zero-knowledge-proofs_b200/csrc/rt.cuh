@@ -107,6 +107,10 @@ G16_HD uint32_t atomic_add_u32(uint32_t *p, uint32_t v) {
 #endif
 }
 
+void note_launch();  // defined in k_misc.cu (one counter for all translation units)
+// number of kernels launched by this library since load (bench.py reports the per-step delta)
+unsigned long long launch_count();
+
 // ---- launch of a per-thread body -------------------------------------------------------
 #ifndef G16_EMU
 template <class Body, class... A>
@@ -120,6 +124,7 @@ inline void launch(size_t n, stream_t s, A... args) {
     size_t blocks = (n + Body::BLOCK - 1) / Body::BLOCK;
     thread_kernel<Body, A...><<<(unsigned)blocks, Body::BLOCK, 0, s>>>(n, args...);
     G16_CUDA_CHECK(cudaGetLastError());
+    note_launch();
 }
 #else
 template <class Body, class... A>

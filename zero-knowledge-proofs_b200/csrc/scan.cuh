@@ -70,10 +70,12 @@ inline void exclusive_scan_u32(const uint32_t *in, uint32_t *out, size_t n, uint
     size_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
     scan_tile_kernel<<<(unsigned)tiles, SCAN_THREADS, 0, s>>>(in, out, tiles > 1 ? tmp : nullptr, n);
     G16_CUDA_CHECK(cudaGetLastError());
+    note_launch();
     if (tiles > 1) {
         exclusive_scan_u32(tmp, tmp, tiles, tmp + tiles, s);
         scan_add_kernel<<<(unsigned)tiles, SCAN_THREADS, 0, s>>>(out, tmp, n);
         G16_CUDA_CHECK(cudaGetLastError());
+        note_launch();
     }
 }
 #else
