@@ -72,6 +72,7 @@ def check_skewed_scalars(ctx, oracle, gens, n, seed):
             sc = np.zeros((n, 4), dtype=np.uint64)
             sc[rng.random(n) < 0.5] = one
         else:
+            # every scalar equal: each window piles all n points into ONE bucket (exercises bucket splitting)
             sc = np.tile(np.array(bls.fr_to_mont(0x1234567), dtype=np.uint64), (n, 1))
         exp, einf = oracle.g1_msm(pts, inf, sc, threads=oracle.max_threads())
         out, oinf = ctx.multi_scalar_mult_g1(sc, pts, inf)

@@ -1,0 +1,69 @@
+"""BASELINE config 1: toy circuits, fixed SetupParams and fixed (r, s).  The engine's prove schedule
+(g16_prove through the C ABI) must give the same proof bytes as the reference-semantics model
+(oracle/groth16_ref.py), and the model's verifier decides whether that proof verifies."""
+import numpy as np
+
+import bls12_381 as bls
+import groth16_ref as ref
+
+
+def pk_to_arrays(pk):
+    def g1s(pts):
+        xy = np.array([bls.g1_to_mont(p)[0] for p in pts], dtype=np.uint64).reshape(-1, 12)
+        inf = np.array([bls.g1_to_mont(p)[1] for p in pts], dtype=np.uint8)
+        return xy, inf
+    def g2s(pts):
+        xy = np.array([bls.g2_to_mont(p)[0] for p in pts], dtype=np.uint64).reshape(-1, 24)
+        inf = np.array([bls.g2_to_mont(p)[1] for p in pts], dtype=np.uint8)
+        return xy, inf
+    d = {"num_public": pk["num_public"]}
+    for k in ("alpha_g1", "beta_g1", "delta_g1"):
+        d[k] = np.array(bls.g1_to_mont(pk[k])[0], dtype=np.uint64)
+    for k in ("beta_g2", "delta_g2"):
+        d[k] = np.array(bls.g2_to_mont(pk[k])[0], dtype=np.uint64)
+    for k in ("a_g1", "b_g1", "ic_g1", "h_g1"):
+        d[k], d[k + "_inf"] = g1s(pk[k])
+    d["b_g2"], d["b_g2_inf"] = g2s(pk["b_g2"])
+    return d
+
+
+def fr_arr(vals):
+    return np.array([bls.fr_to_mont(v) for v in vals], dtype=np.uint64).reshape(-1, 4)
+
+
+def gpu_prove(ctx, pk, assignment, r, s):
+    """Host side of Prover::prove up to the MSMs (truncation + quotient, lib.rs:149-208) from the model,
+    group part on the engine."""
+    w, h = ref.prover_inputs(pk, assignment)
+    dev_pk = ctx.pk_upload(pk_to_arrays(pk))
+    (a, ai), (b, bi), (c, ci) = ctx.prove(dev_pk, fr_arr(w), fr_arr(h) if h else None, fr_arr([r])[0], fr_arr([s])[0])
+    dev_pk.free()
+    return (bls.g1_from_mont(list(a), ai), bls.g2_from_mont(list(b), bi), bls.g1_from_mont(list(c), ci))
+
+
+CASES = [
+    # (name, circuit, params, expected verifier verdict under reference semantics -- SURVEY.md App. C)
+    ("mul_Pverify", ref.circuit_mul, ref.P_VERIFY, True),
+    ("mul_Prand", ref.circuit_mul, ref.P_RAND, False),
+    ("cubic_Pverify", ref.circuit_cubic, ref.P_VERIFY, False),
+    ("cubic_Prand", ref.circuit_cubic, ref.P_RAND, False),
+]
+
+
+def check_config1(ctx, golden=None):
+    out = {}
+    for name, circuit, params, verdict in CASES:
+        constraints, nvars, w, npub = circuit()
+        qap = ref.QAP(constraints, nvars)
+        pk, vk = ref.setup(qap, params, npub)
+        expect = ref.prove(pk, w, ref.FIXED_R, ref.FIXED_S)
+        got = gpu_prove(ctx, pk, w, ref.FIXED_R, ref.FIXED_S)
+        assert ref.proof_to_bytes(got) == ref.proof_to_bytes(expect), name
+        assert len(ref.proof_to_bytes(got)) == 192 and len(ref.proof_to_bytes(got, compressed=False)) == 384
+        assert ref.verify(vk, got, w[1:npub + 1]) is verdict, name
+        if verdict:   # a wrong public input must not verify (test_invalid_proof, lib.rs:483-511)
+            assert ref.verify(vk, got, [w[1] + 1]) is False
+        out[name] = ref.proof_to_bytes(got).hex()
+        if golden is not None:
+            assert golden[name] == out[name], name
+    return out

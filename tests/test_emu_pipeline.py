@@ -30,3 +30,4 @@ def test_emu_adversarial_and_skewed(emu_ctx, oracle, gens):
     pc.check_adversarial(emu_ctx, oracle, gens, "g1", 300, 5)
     pc.check_adversarial(emu_ctx, oracle, gens, "g2", 60, 6)
     pc.check_skewed_scalars(emu_ctx, oracle, gens, 200, 7)
+    pc.check_skewed_scalars(emu_ctx, oracle, gens, 1500, 8)   # > ITEM_MAX entries per bucket: split + merge path

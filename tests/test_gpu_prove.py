@@ -1,0 +1,24 @@
+"""BASELINE config 1 on the GPU: toy circuits, fixed SetupParams, fixed (r, s) -> proof bytes identical
+to the reference-semantics model and to the committed golden fixture; verdict from the model's verifier."""
+import json
+import os
+
+import pytest
+
+import prove_cases
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "config1_proofs.json")
+
+
+def test_config1_proofs_bit_exact(gpu_ctx):
+    prove_cases.check_config1(gpu_ctx, json.load(open(GOLDEN)))
+
+
+def test_config1_proofs_multi_shard_context():
+    import groth16_cuda
+    ctx = groth16_cuda.Context(devices=[0, 0])     # two index-range shards (one GPU is enough for the code path)
+    try:
+        prove_cases.check_config1(ctx, json.load(open(GOLDEN)))
+    finally:
+        ctx.close()

@@ -13,11 +13,11 @@ enum Group { GROUP_G1 = 1, GROUP_G2 = 2 };
 template <class F> struct GroupOf { static constexpr int id = FieldWords<F>::group; };
 
 struct Workspace {
-    DevBuf scalars, counts, cursor, entries, buckets, red[4], scan_tmp, out, partials, staging;
+    DevBuf scalars, counts, codes, bins, items, item_start, chunk_out, cursor, entries, buckets, red[4], scan_tmp, out, partials, staging;
     DevBuf fb_base, fb_powers, fb_table[3], fb_out, fb_flags;
     std::vector<uint32_t> fb_table_key[3];  // base limbs the cached table was built for
     void release() {
-        scalars.release(); counts.release(); cursor.release(); entries.release(); buckets.release();
+        scalars.release(); counts.release(); codes.release(); bins.release(); items.release(); item_start.release(); chunk_out.release(); cursor.release(); entries.release(); buckets.release();
         for (auto &r : red) r.release();
         scan_tmp.release(); out.release(); partials.release(); staging.release();
         fb_base.release(); fb_powers.release(); fb_out.release(); fb_flags.release();
@@ -27,7 +27,7 @@ struct Workspace {
 
 // optional per-stage CUDA-event timing of the last MSM on a device (bench.py reads it to put the
 // dominant kernel's measured duration into the roofline line)
-constexpr int N_STAGES = 6;  // count, scan, scatter, accumulate, reduce, combine
+constexpr int N_STAGES = 6;  // digits, scan+items, scatter, accumulate, reduce, combine
 struct StageTimer {
     bool enabled = false;
 #ifndef G16_EMU
@@ -132,7 +132,6 @@ inline MsmPlan make_plan(size_t n, unsigned c_override, size_t point_words) {
     return p;
 }
 
-constexpr uint32_t REDUCE_L = 32;  // group size of one reduction level
 constexpr uint32_t REDUCE_LOG_L = 5;
 
 // One MSM on one device, asynchronous on dv.stream.
@@ -154,38 +153,60 @@ void msm_run(Device &dv, const uint32_t *pts, const uint32_t *d_scalars, size_t 
     if ((double)n * plan.nwin >= 4294967295.0) throw Error{G16_ERR_INVALID, "n * windows exceeds 2^32 entries"};
 
     dv.last_plan = plan;
+    size_t max_entries = n * plan.nwin;
     dv.timer.mark(0, s);
-    // 1. bucket sizes
+    // 1. canonical scalars -> signed digits: bucket histogram + per-window code array
     uint32_t *counts = ws.counts.as<uint32_t>(total + 1);
     dev_memset(counts, 0, (total + 1) * sizeof(uint32_t), s);
-    k_digit_count(s, n, d_scalars, mont, plan, counts);
+    uint32_t *codes = ws.codes.as<uint32_t>(max_entries);
+    k_digit_decompose(s, n, d_scalars, mont, plan, counts, codes);
     dv.timer.mark(1, s);
-    // 2. bucket offsets (exclusive scan; offsets[total] = number of entries)
+    // 2. bucket offsets (exclusive scan; offsets[total] = number of entries) and the work-item list
+    //    (bucket slices ordered by length, longest first)
     uint32_t *scan_tmp = ws.scan_tmp.as<uint32_t>(k_scan_tmp_words(total + 1));
     k_exclusive_scan(s, counts, counts, total + 1, scan_tmp);
     uint32_t *offsets = counts;
+    size_t nbins = k_item_bins();
+    uint32_t *bins = ws.bins.as<uint32_t>(2 * (nbins + 1));
+    uint32_t *bin_cursor = bins + nbins + 1;
+    dev_memset(bins, 0, (nbins + 1) * sizeof(uint32_t), s);
+    k_item_count(s, total, offsets, bins);
+    k_exclusive_scan(s, bins, bins, nbins + 1, scan_tmp);
+    copy_d2d(bin_cursor, bins, (nbins + 1) * sizeof(uint32_t), s);
+    size_t max_split = max_entries / (k_item_max() / 2) + 16;
+    size_t max_items = total + max_split;
+    WorkItem *items = (WorkItem *)ws.items.need(max_items * k_item_bytes());
+    uint32_t *item_start = ws.item_start.as<uint32_t>(total);
+    k_item_scatter(s, total, offsets, bin_cursor, items, item_start);
     dv.timer.mark(2, s);
-    // 3. scatter (point index, sign) into bucket order
+    // 3. counting-sort scatter of (point index, sign) into bucket order, one window at a time
     uint32_t *cursor = ws.cursor.as<uint32_t>(total);
     copy_d2d(cursor, offsets, total * sizeof(uint32_t), s);
-    uint32_t *entries = ws.entries.as<uint32_t>(n * plan.nwin);
-    k_digit_scatter(s, n, d_scalars, mont, plan, cursor, entries);
+    uint32_t *entries = ws.entries.as<uint32_t>(max_entries);
+    k_scatter_by_window(s, n, codes, plan, cursor, entries);
     dv.timer.mark(3, s);
-    // 4. bucket accumulation (the hot kernel)
+    // 4. bucket accumulation (the hot kernel) + fold of split buckets
     uint32_t *buckets = ws.buckets.as<uint32_t>(total * 4 * FieldWords<F>::N);
-    k_accumulate<F>(s, total, pts, entries, offsets, buckets);
+    uint32_t *chunk_out = ws.chunk_out.as<uint32_t>(max_split * 4 * FieldWords<F>::N);
+    k_accumulate<F>(s, max_items, pts, entries, items, bins + nbins, buckets, chunk_out);
+    k_chunk_merge<F>(s, total, offsets, item_start, chunk_out, buckets);
     dv.timer.mark(4, s);
     // 5. parallel bucket reduction
     const uint32_t *X = buckets, *Y = nullptr;
-    uint32_t n_in = plan.nb, level = 0;
+    uint32_t n_in = plan.nb, shift = 0;
     int flip = 0;
     while (n_in > 1) {
-        uint32_t n_out = (n_in + REDUCE_L - 1) / REDUCE_L;
+        // group size 2^log_l: 32 while there is plenty of parallelism (least total work), smaller near the
+        // top of the tree where the level is latency bound (one thread walks 2^log_l entries serially)
+        uint32_t log_l = REDUCE_LOG_L;
+        while (log_l > 2 && (size_t)plan.nwin * ((n_in + (1u << log_l) - 1) >> log_l) < 16384) --log_l;
+        uint32_t L = 1u << log_l;
+        uint32_t n_out = (n_in + L - 1) / L;
         uint32_t *Xo = ws.red[flip].as<uint32_t>((size_t)plan.nwin * n_out * 4 * FieldWords<F>::N);
         uint32_t *Yo = ws.red[flip + 1].as<uint32_t>((size_t)plan.nwin * n_out * 4 * FieldWords<F>::N);
-        k_reduce_level<F>(s, (size_t)plan.nwin * n_out, X, Y, n_in, n_out, REDUCE_L, REDUCE_LOG_L * level, Xo, Yo);
+        k_reduce_level<F>(s, (size_t)plan.nwin * n_out, X, Y, n_in, n_out, L, shift, Xo, Yo);
         X = Xo; Y = Yo;
-        n_in = n_out; ++level; flip ^= 2;
+        n_in = n_out; shift += log_l; flip ^= 2;
     }
     dv.timer.mark(5, s);
     // 6. window fold + to affine

@@ -6,12 +6,22 @@ namespace g16 {
 static std::atomic<unsigned long long> g_launches{0};
 void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 unsigned long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
-void k_digit_count(stream_t s, size_t n, const uint32_t *scalars, bool mont, MsmPlan plan, uint32_t *counts) {
-    launch<DigitCount>(n, s, scalars, mont, plan, counts);
+void k_digit_decompose(stream_t s, size_t n, const uint32_t *scalars, bool mont, MsmPlan plan, uint32_t *counts,
+                        uint32_t *codes) {
+    launch<DigitDecompose>(n, s, scalars, mont, plan, n, counts, codes);
 }
-void k_digit_scatter(stream_t s, size_t n, const uint32_t *scalars, bool mont, MsmPlan plan, uint32_t *cursor,
-                     uint32_t *entries) {
-    launch<DigitScatter>(n, s, scalars, mont, plan, cursor, entries);
+void k_scatter_by_window(stream_t s, size_t n, const uint32_t *codes, MsmPlan plan, uint32_t *cursor, uint32_t *entries) {
+    launch<ScatterByWindow>(n * plan.nwin, s, codes, plan, n, cursor, entries);
+}
+size_t k_item_bins() { return ITEM_BINS; }
+size_t k_item_bytes() { return sizeof(WorkItem); }
+uint32_t k_item_max() { return ITEM_MAX; }
+void k_item_count(stream_t s, size_t buckets, const uint32_t *offsets, uint32_t *bin_counts) {
+    launch<ItemCount>(buckets, s, offsets, bin_counts);
+}
+void k_item_scatter(stream_t s, size_t buckets, const uint32_t *offsets, uint32_t *bin_cursor, WorkItem *items,
+                    uint32_t *item_start) {
+    launch<ItemScatter>(buckets, s, offsets, bin_cursor, items, item_start);
 }
 size_t k_scan_tmp_words(size_t n) { return scan_tmp_words(n); }
 void k_exclusive_scan(stream_t s, const uint32_t *in, uint32_t *out, size_t n, uint32_t *tmp) {

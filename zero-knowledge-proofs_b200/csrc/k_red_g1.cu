@@ -1,4 +1,4 @@
 // cold kernel: bucket reduction level (g1)
-#define G16_COLD 1
+// hot: field multiply inlined (G1 tail latency matters at small N and in strong scaling)
 #include "kernel_impl.cuh"
 namespace g16 { template void k_reduce_level<Fq>(stream_t, size_t, const uint32_t *, const uint32_t *, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t *, uint32_t *); }

@@ -24,15 +24,26 @@ template <> struct FieldWords<Fq> { static constexpr size_t N = 12; static const
 template <> struct FieldWords<Fq2> { static constexpr size_t N = 24; static constexpr int group = 2; };
 
 // scalars -> bucket histogram / bucket-ordered entries
-void k_digit_count(stream_t s, size_t n, const uint32_t *scalars, bool mont, MsmPlan plan, uint32_t *counts);
-void k_digit_scatter(stream_t s, size_t n, const uint32_t *scalars, bool mont, MsmPlan plan, uint32_t *cursor,
-                     uint32_t *entries);
+void k_digit_decompose(stream_t s, size_t n, const uint32_t *scalars, bool mont, MsmPlan plan, uint32_t *counts,
+                        uint32_t *codes);
+void k_scatter_by_window(stream_t s, size_t n, const uint32_t *codes, MsmPlan plan, uint32_t *cursor, uint32_t *entries);
+// work items (bucket slices ordered by length); see msm_kernels.cuh
+struct WorkItem;
+size_t k_item_bins();
+size_t k_item_bytes();
+uint32_t k_item_max();
+void k_item_count(stream_t s, size_t buckets, const uint32_t *offsets, uint32_t *bin_counts);
+void k_item_scatter(stream_t s, size_t buckets, const uint32_t *offsets, uint32_t *bin_cursor, WorkItem *items,
+                    uint32_t *item_start);
 size_t k_scan_tmp_words(size_t n);
 void k_exclusive_scan(stream_t s, const uint32_t *in, uint32_t *out, size_t n, uint32_t *tmp);
 
 template <class F>
-void k_accumulate(stream_t s, size_t items, const uint32_t *pts, const uint32_t *entries, const uint32_t *offsets,
-                  uint32_t *buckets);
+void k_accumulate(stream_t s, size_t max_items, const uint32_t *pts, const uint32_t *entries, const WorkItem *work,
+                  const uint32_t *n_items, uint32_t *buckets, uint32_t *chunk_out);
+template <class F>
+void k_chunk_merge(stream_t s, size_t buckets_n, const uint32_t *offsets, const uint32_t *item_start,
+                   const uint32_t *chunk_out, uint32_t *buckets);
 template <class F>
 void k_reduce_level(stream_t s, size_t threads, const uint32_t *X, const uint32_t *Y, uint32_t n_in, uint32_t n_out,
                     uint32_t L, uint32_t shift, uint32_t *Xo, uint32_t *Yo);

@@ -7,9 +7,14 @@
 namespace g16 {
 
 template <class F>
-void k_accumulate(stream_t s, size_t items, const uint32_t *pts, const uint32_t *entries, const uint32_t *offsets,
-                  uint32_t *buckets) {
-    launch<BucketAccumulate<F>>(items, s, pts, entries, offsets, buckets);
+void k_accumulate(stream_t s, size_t max_items, const uint32_t *pts, const uint32_t *entries, const WorkItem *work,
+                  const uint32_t *n_items, uint32_t *buckets, uint32_t *chunk_out) {
+    launch<BucketAccumulate<F>>(max_items, s, pts, entries, work, n_items, buckets, chunk_out);
+}
+template <class F>
+void k_chunk_merge(stream_t s, size_t buckets_n, const uint32_t *offsets, const uint32_t *item_start,
+                   const uint32_t *chunk_out, uint32_t *buckets) {
+    launch<ChunkMerge<F>>(buckets_n, s, offsets, item_start, chunk_out, buckets);
 }
 template <class F>
 void k_reduce_level(stream_t s, size_t threads, const uint32_t *X, const uint32_t *Y, uint32_t n_in, uint32_t n_out,

@@ -44,37 +44,92 @@ G16_HD void load_scalar(const uint32_t *scalars, size_t i, bool mont, uint32_t o
     for (int j = 0; j < 8; ++j) out[j] = s.l[j];
 }
 
-struct DigitCount {
+// Bucket code of one (scalar, window) digit: bucket index | sign << 31, or NO_DIGIT for a zero digit.
+constexpr uint32_t NO_DIGIT = 0xffffffffu;
+
+// One thread per scalar: canonical form, signed digits, bucket histogram, and the per-window code
+// array codes[w * n + i] (window-major so that the scatter pass below streams it coalesced).
+struct DigitDecompose {
     static constexpr int BLOCK = 256;
-    G16_HD static void run(size_t i, const uint32_t *scalars, bool mont, MsmPlan plan, uint32_t *counts) {
+    G16_HD static void run(size_t i, const uint32_t *scalars, bool mont, MsmPlan plan, size_t n, uint32_t *counts,
+                           uint32_t *codes) {
         uint32_t k[8];
         load_scalar(scalars, i, mont, k);
         DigitIter it(k, plan.c);
         for (uint32_t w = 0; w < plan.nwin; ++w) {
             int32_t d = it.next();
+            uint32_t code = NO_DIGIT;
             if (d != 0) {
                 uint32_t b = (uint32_t)(d < 0 ? -d : d) - 1u;
                 atomic_add_u32(&counts[w * plan.nb + b], 1u);
+                code = b | (d < 0 ? 0x80000000u : 0u);
             }
+            codes[(size_t)w * n + i] = code;
         }
     }
 };
 
+// Counting-sort scatter, one thread per (window, scalar), window-major: all writes of one window land
+// in an n x 4 B slice of `entries` (64 MB at n = 2^24, i.e. L2 resident) before the next window starts.
 // entries[cursor[bucket]++] = point index | sign << 31
-struct DigitScatter {
+struct ScatterByWindow {
     static constexpr int BLOCK = 256;
-    G16_HD static void run(size_t i, const uint32_t *scalars, bool mont, MsmPlan plan, uint32_t *cursor,
-                           uint32_t *entries) {
-        uint32_t k[8];
-        load_scalar(scalars, i, mont, k);
-        DigitIter it(k, plan.c);
-        for (uint32_t w = 0; w < plan.nwin; ++w) {
-            int32_t d = it.next();
-            if (d != 0) {
-                uint32_t b = (uint32_t)(d < 0 ? -d : d) - 1u;
-                uint32_t pos = atomic_add_u32(&cursor[w * plan.nb + b], 1u);
-                entries[pos] = (uint32_t)i | (d < 0 ? 0x80000000u : 0u);
-            }
+    G16_HD static void run(size_t t, const uint32_t *codes, MsmPlan plan, size_t n, uint32_t *cursor, uint32_t *entries) {
+        uint32_t code = codes[t];
+        if (code == NO_DIGIT) return;
+        uint32_t w = (uint32_t)(t / n), i = (uint32_t)(t % n);
+        uint32_t pos = atomic_add_u32(&cursor[w * plan.nb + (code & 0x7fffffffu)], 1u);
+        entries[pos] = i | (code & 0x80000000u);
+    }
+};
+
+// ---- work items ------------------------------------------------------------------------------------
+// A work item is a slice [begin, end) of one bucket's entries.  Buckets of up to ITEM_MAX entries are
+// one item; longer ones are split into chunks of about max(ITEM_MAX, sqrt(size)) entries so that a
+// skewed scalar distribution (boolean witnesses, repeated values) cannot serialise on one thread.
+// Items are ordered by length, longest first, so the 32 lanes of a warp run loops of (nearly) equal
+// length -- with Poisson-distributed bucket sizes this removes most of the divergence loss.
+constexpr uint32_t ITEM_MAX = 256;
+constexpr uint32_t ITEM_BINS = ITEM_MAX + 2;   // bin 0: chunks of split buckets, bin 1 + (ITEM_MAX - len): whole buckets
+struct WorkItem { uint32_t begin, end, bucket; };  // bucket | SPLIT_FLAG when it is a chunk
+constexpr uint32_t SPLIT_FLAG = 0x80000000u;
+
+G16_HD uint32_t isqrt_ceil(uint32_t v) {
+    uint32_t r = 1;
+    while ((uint64_t)r * r < v) r <<= 1;          // power of two >= sqrt(v): cheap and good enough
+    return r;
+}
+G16_HD void item_shape(uint32_t size, uint32_t &nch, uint32_t &len, uint32_t &bin) {
+    if (size <= ITEM_MAX) { nch = 1; len = size; bin = 1u + (ITEM_MAX - size); return; }
+    uint32_t target = isqrt_ceil(size);
+    if (target < ITEM_MAX) target = ITEM_MAX;
+    nch = (size + target - 1) / target;
+    len = (size + nch - 1) / nch;
+    bin = 0;
+}
+
+struct ItemCount {
+    static constexpr int BLOCK = 256;
+    G16_HD static void run(size_t g, const uint32_t *offsets, uint32_t *bin_counts) {
+        uint32_t nch, len, bin;
+        item_shape(offsets[g + 1] - offsets[g], nch, len, bin);
+        atomic_add_u32(&bin_counts[bin], nch);
+    }
+};
+
+struct ItemScatter {
+    static constexpr int BLOCK = 256;
+    G16_HD static void run(size_t g, const uint32_t *offsets, uint32_t *bin_cursor, WorkItem *items, uint32_t *item_start) {
+        uint32_t begin = offsets[g], size = offsets[g + 1] - begin;
+        uint32_t nch, len, bin;
+        item_shape(size, nch, len, bin);
+        uint32_t pos = atomic_add_u32(&bin_cursor[bin], nch);
+        item_start[g] = pos;
+        for (uint32_t j = 0; j < nch; ++j) {
+            uint32_t b = begin + j * len;
+            uint32_t e = b + len < begin + size ? b + len : begin + size;
+            if (b > begin + size) b = begin + size;
+            items[pos + j] = WorkItem{b, e, (uint32_t)g | (nch > 1 ? SPLIT_FLAG : 0u)};
         }
     }
 };
@@ -133,23 +188,44 @@ G16_HD XYZZ<F> load_xyzz(const uint32_t *src, size_t idx) {
     return p;
 }
 
-// One thread per work item.  A work item is (bucket, [begin, end)) -- a whole bucket, or a
-// slice of an oversized bucket (see engine: buckets longer than the chunk limit are split so
-// that skewed scalar distributions cannot serialise on one thread).
+// The hot kernel: one thread per work item.  Whole buckets are written straight to `buckets`; chunks of
+// split buckets go to chunk_out[item index] (split items occupy the front of the item array) and are
+// folded by ChunkMerge.
 template <class F>
 struct BucketAccumulate {
     static constexpr int BLOCK = 128;
-    G16_HD static void run(size_t t, const uint32_t *pts, const uint32_t *entries, const uint32_t *offsets,
-                           uint32_t *buckets) {
-        uint32_t begin = offsets[t], end = offsets[t + 1];
+    G16_HD static void run(size_t t, const uint32_t *pts, const uint32_t *entries, const WorkItem *items,
+                           const uint32_t *n_items, uint32_t *buckets, uint32_t *chunk_out) {
+        if (t >= *n_items) return;   // the launch covers an upper bound; the exact count lives on the device
+        WorkItem it = items[t];
         XYZZ<F> acc = XYZZ<F>::inf();
-        for (uint32_t e = begin; e < end; ++e) {
+        for (uint32_t e = it.begin; e < it.end; ++e) {
             uint32_t v = entries[e];
             Affine<F> p = load_affine<F>(pts, v & 0x7fffffffu);
             if (v >> 31) p.y = F::neg(p.y);
             xyzz_madd(acc, p.x, p.y);
         }
-        store_xyzz<F>(buckets, t, acc);
+        if (it.bucket & SPLIT_FLAG) store_xyzz<F>(chunk_out, t, acc);
+        else store_xyzz<F>(buckets, it.bucket, acc);
+    }
+};
+
+// One thread per bucket: buckets that were split get the sum of their chunk partials.
+template <class F>
+struct ChunkMerge {
+    static constexpr int BLOCK = 128;
+    G16_HD static void run(size_t g, const uint32_t *offsets, const uint32_t *item_start, const uint32_t *chunk_out,
+                           uint32_t *buckets) {
+        uint32_t nch, len, bin;
+        item_shape(offsets[g + 1] - offsets[g], nch, len, bin);
+        if (nch == 1) return;
+        XYZZ<F> acc = XYZZ<F>::inf();
+        uint32_t first = item_start[g];
+        for (uint32_t j = 0; j < nch; ++j) {
+            XYZZ<F> p = load_xyzz<F>(chunk_out, first + j);
+            xyzz_add(acc, p);
+        }
+        store_xyzz<F>(buckets, g, acc);
     }
 };
 
