@@ -66,6 +66,11 @@ int g16_g2_bases_upload(g16_ctx *ctx, const uint64_t *xy, const uint8_t *inf, si
  * (0,0) meaning infinity -- e.g. the output of g16_g1_fixed_base_mul_device.  Not owned. */
 int g16_g1_bases_from_device(g16_ctx *ctx, const void *dev_xy, size_t n, g16_bases **out);
 int g16_g2_bases_from_device(g16_ctx *ctx, const void *dev_xy, size_t n, g16_bases **out);
+/* One-time preprocessing of resident bases (CRS arrays are fixed per ProvingKey): stores the multiples
+ * 2^(c w) P_i for every window w, so that all windows of an MSM feed one shared bucket set -- no Horner
+ * fold, one bucket reduction instead of ceil(256/c).  window_bits = 0 chooses c from the array length and
+ * budget_bytes (0 = 48 GiB) of device memory per shard; *used_bits receives c.  Results are unchanged. */
+int g16_bases_precompute(g16_ctx *ctx, g16_bases *bases, unsigned window_bits, size_t budget_bytes, unsigned *used_bits);
 void g16_bases_free(g16_bases *bases);
 size_t g16_bases_len(const g16_bases *bases);
 

@@ -33,7 +33,7 @@ def check_empty(ctx):
     assert inf == 1 and not out.any()
 
 
-def check_random_msm(ctx, oracle, gens, group, n, seed, windows=(0,)):
+def check_random_msm(ctx, oracle, gens, group, n, seed, windows=(0,), pre=()):
     pts, inf = helpers.make_points(oracle, gens, group, 0xba5e0000 + seed, n)
     sc = oracle.gen_scalars(0x5eed0000 + seed, n)
     exp, einf = (oracle.g1_msm if group == "g1" else oracle.g2_msm)(pts, inf, sc, threads=oracle.max_threads())
@@ -43,6 +43,12 @@ def check_random_msm(ctx, oracle, gens, group, n, seed, windows=(0,)):
         out, oinf = (ctx.g1_msm if group == "g1" else ctx.g2_msm)(bases, sc)
         assert oinf == einf and (out == exp).all(), (group, n, c)
     ctx.set_window_bits(0)
+    # resident bases with precomputed multiples 2^(c w) P: same group element
+    for pc_bits in pre:
+        used = bases.precompute(pc_bits)
+        assert used == (pc_bits or used) and 8 <= used <= 24
+        out, oinf = (ctx.g1_msm if group == "g1" else ctx.g2_msm)(bases, sc)
+        assert oinf == einf and (out == exp).all(), (group, n, "precompute", pc_bits)
     # prefix of the resident bases (n' < len(bases))
     m = max(1, n // 3)
     exp, einf = (oracle.g1_msm if group == "g1" else oracle.g2_msm)(pts[:m], inf[:m], sc[:m])

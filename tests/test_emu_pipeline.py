@@ -22,8 +22,8 @@ def test_emu_field_and_group_hooks(emu_ctx, oracle, gens):
 
 
 def test_emu_random_and_window_sweep(emu_ctx, oracle, gens):
-    pc.check_random_msm(emu_ctx, oracle, gens, "g1", 257, 1, windows=(0, 2, 3, 7, 11, 16))
-    pc.check_random_msm(emu_ctx, oracle, gens, "g2", 40, 2, windows=(0, 5))
+    pc.check_random_msm(emu_ctx, oracle, gens, "g1", 257, 1, windows=(0, 2, 3, 7, 11, 16), pre=(8, 13, 0))
+    pc.check_random_msm(emu_ctx, oracle, gens, "g2", 40, 2, windows=(0, 5), pre=(9,))
 
 
 def test_emu_adversarial_and_skewed(emu_ctx, oracle, gens):

@@ -42,17 +42,17 @@ def test_g1_small_sizes(gpu_ctx, oracle, gens, n):
 
 
 def test_g1_window_sweep(gpu_ctx, oracle, gens):
-    pc.check_random_msm(gpu_ctx, oracle, gens, "g1", 3000, 3, windows=(0, 2, 3, 5, 8, 11, 13, 16, 20))
+    pc.check_random_msm(gpu_ctx, oracle, gens, "g1", 3000, 3, windows=(0, 2, 3, 5, 8, 11, 13, 16, 20), pre=(8, 12, 16, 0))
 
 
 def test_g1_2_16_config2(gpu_ctx, oracle, gens):
     """BASELINE config 2: standalone G1 MSM, 2^16 random scalars/points."""
-    pc.check_random_msm(gpu_ctx, oracle, gens, "g1", 1 << 16, 16)
+    pc.check_random_msm(gpu_ctx, oracle, gens, "g1", 1 << 16, 16, pre=(0,))
 
 
 @pytest.mark.parametrize("n", [1, 2, 3, 40, 1 << 12])
 def test_g2_sizes(gpu_ctx, oracle, gens, n):
-    pc.check_random_msm(gpu_ctx, oracle, gens, "g2", n, 100 + n, windows=(0, 7) if n == 40 else (0,))
+    pc.check_random_msm(gpu_ctx, oracle, gens, "g2", n, 100 + n, windows=(0, 7) if n == 40 else (0,), pre=(0,) if n >= 40 else ())
 
 
 def test_adversarial_sets(gpu_ctx, oracle, gens):

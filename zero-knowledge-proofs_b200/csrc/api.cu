@@ -190,6 +190,16 @@ int g16_g1_bases_from_device(g16_ctx *ctx, const void *dev_xy, size_t n, g16_bas
 int g16_g2_bases_from_device(g16_ctx *ctx, const void *dev_xy, size_t n, g16_bases **out) {
     return bases_from_device_impl<Fq2>(ctx, dev_xy, n, out);
 }
+int g16_bases_precompute(g16_ctx *ctx, g16_bases *bases, unsigned window_bits, size_t budget_bytes, unsigned *used_bits) {
+    if (!ctx || !bases) return G16_ERR_INVALID;
+    return guarded(ctx, [&] {
+        require(bases->b->ctx == &ctx->c, "bases belong to another context");
+        if (budget_bytes == 0) budget_bytes = (size_t)48 << 30;
+        unsigned c = bases->b->group == GROUP_G1 ? bases_precompute<Fq>(&ctx->c, bases->b.get(), window_bits, budget_bytes)
+                                                 : bases_precompute<Fq2>(&ctx->c, bases->b.get(), window_bits, budget_bytes);
+        if (used_bits) *used_bits = c;
+    });
+}
 void g16_bases_free(g16_bases *bases) { delete bases; }
 size_t g16_bases_len(const g16_bases *bases) { return bases ? bases->b->n : 0; }
 
@@ -249,7 +259,7 @@ static int msm_device_impl(g16_ctx *ctx, const g16_bases *bases, const void *dev
         require(bases->b->shards.size() == 1, "bases are sharded");
         if (n > bases->b->n) throw Error{G16_ERR_LENGTH, "more scalars than bases"};
         require(dev_scalars || n == 0, "dev_scalars is NULL");
-        msm_run<F>(dv, bases->b->shards[0].pts, (const uint32_t *)dev_scalars, n, true, ctx->c.c_override,
+        msm_run<F>(dv, bases->b->shards[0], (const uint32_t *)dev_scalars, n, true, ctx->c.c_override,
                    (uint32_t *)dev_out_partial, (uint32_t *)dev_out_affine);
     });
 }

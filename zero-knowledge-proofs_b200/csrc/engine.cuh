@@ -94,6 +94,9 @@ struct BasesShard {
     uint32_t *pts = nullptr;
     size_t begin = 0, n = 0;
     bool owned = true;
+    // optional precomputed multiples: table[w * n + i] = 2^(pre_c w) P_i, w < ceil(256 / pre_c)
+    uint32_t *table = nullptr;
+    unsigned pre_c = 0;
 };
 
 struct Bases {
@@ -103,7 +106,11 @@ struct Bases {
     std::vector<BasesShard> shards;
     ~Bases() {
         for (auto &s : shards)
-            if (s.owned && s.pts) { set_device(ctx->devs[s.dev].id); dev_free(s.pts); }
+        {
+            if ((s.owned && s.pts) || s.table) set_device(ctx->devs[s.dev].id);
+            if (s.owned && s.pts) dev_free(s.pts);
+            if (s.table) dev_free(s.table);
+        }
     }
 };
 
@@ -129,7 +136,36 @@ inline MsmPlan make_plan(size_t n, unsigned c_override, size_t point_words) {
     p.nwin = (256 + best_c - 1) / best_c;
     p.nb = 1u << (best_c - 1);
     p.total = p.nwin * p.nb;
+    p.bwin = p.nwin;
+    p.stride = 0;
     return p;
+}
+
+// plan for bases that carry precomputed multiples for window size c
+inline MsmPlan make_shared_plan(unsigned c, size_t stride) {
+    MsmPlan p;
+    p.c = c;
+    p.nwin = (256 + c - 1) / c;
+    p.nb = 1u << (c - 1);
+    p.total = p.nb;
+    p.bwin = 1;
+    p.stride = (uint32_t)stride;
+    return p;
+}
+
+// window size for a precomputed table over n bases: every digit costs one mixed addition, the single
+// shared bucket set costs two full additions per bucket; the table must fit `budget` bytes and 31 bits.
+inline unsigned choose_precompute_c(size_t n, size_t point_bytes, size_t budget) {
+    unsigned best_c = 0;
+    double best = 1e300;
+    for (unsigned c = 8; c <= 24; ++c) {
+        double nwin = (256 + c - 1) / c;
+        if (nwin * (double)n * point_bytes > (double)budget) continue;
+        if (nwin * (double)n >= 2147483648.0) continue;
+        double cost = nwin * (double)n * 10.0 + (double)(1ull << (c - 1)) * 30.0;
+        if (cost < best) { best = cost; best_c = c; }
+    }
+    return best_c;
 }
 
 constexpr uint32_t REDUCE_LOG_L = 5;
@@ -139,8 +175,9 @@ constexpr uint32_t REDUCE_LOG_L = 5;
 //   d_scalars  : n x 8 u32 on this device
 //   d_out_xyzz : 4*FieldWords<F>::N words (may be null), d_out_aff : 2*FieldWords<F>::N + 1 words (may be null)
 template <class F>
-void msm_run(Device &dv, const uint32_t *pts, const uint32_t *d_scalars, size_t n, bool mont, unsigned c_override,
+void msm_run(Device &dv, const BasesShard &sh, const uint32_t *d_scalars, size_t n, bool mont, unsigned c_override,
              uint32_t *d_out_xyzz, uint32_t *d_out_aff) {
+    const uint32_t *pts = sh.table ? sh.table : sh.pts;
     stream_t s = dv.stream;
     Workspace &ws = dv.ws;
     if (n == 0) {
@@ -148,7 +185,7 @@ void msm_run(Device &dv, const uint32_t *pts, const uint32_t *d_scalars, size_t 
         return;
     }
     if (n >= (1ull << 31)) throw Error{G16_ERR_INVALID, "MSM length must be < 2^31"};
-    MsmPlan plan = make_plan(n, c_override, 2 * FieldWords<F>::N);
+    MsmPlan plan = sh.table ? make_shared_plan(sh.pre_c, sh.n) : make_plan(n, c_override, 2 * FieldWords<F>::N);
     size_t total = plan.total;
     if ((double)n * plan.nwin >= 4294967295.0) throw Error{G16_ERR_INVALID, "n * windows exceeds 2^32 entries"};
 
@@ -199,18 +236,18 @@ void msm_run(Device &dv, const uint32_t *pts, const uint32_t *d_scalars, size_t 
         // group size 2^log_l: 32 while there is plenty of parallelism (least total work), smaller near the
         // top of the tree where the level is latency bound (one thread walks 2^log_l entries serially)
         uint32_t log_l = REDUCE_LOG_L;
-        while (log_l > 2 && (size_t)plan.nwin * ((n_in + (1u << log_l) - 1) >> log_l) < 16384) --log_l;
+        while (log_l > 2 && (size_t)plan.bwin * ((n_in + (1u << log_l) - 1) >> log_l) < 16384) --log_l;
         uint32_t L = 1u << log_l;
         uint32_t n_out = (n_in + L - 1) / L;
-        uint32_t *Xo = ws.red[flip].as<uint32_t>((size_t)plan.nwin * n_out * 4 * FieldWords<F>::N);
-        uint32_t *Yo = ws.red[flip + 1].as<uint32_t>((size_t)plan.nwin * n_out * 4 * FieldWords<F>::N);
-        k_reduce_level<F>(s, (size_t)plan.nwin * n_out, X, Y, n_in, n_out, L, shift, Xo, Yo);
+        uint32_t *Xo = ws.red[flip].as<uint32_t>((size_t)plan.bwin * n_out * 4 * FieldWords<F>::N);
+        uint32_t *Yo = ws.red[flip + 1].as<uint32_t>((size_t)plan.bwin * n_out * 4 * FieldWords<F>::N);
+        k_reduce_level<F>(s, (size_t)plan.bwin * n_out, X, Y, n_in, n_out, L, shift, Xo, Yo);
         X = Xo; Y = Yo;
         n_in = n_out; shift += log_l; flip ^= 2;
     }
     dv.timer.mark(5, s);
     // 6. window fold + to affine
-    k_window_combine<F>(s, X, Y, plan.nwin, plan.c, d_out_xyzz, d_out_aff);
+    k_window_combine<F>(s, X, Y, plan.bwin, plan.c, d_out_xyzz, d_out_aff);
     dv.timer.mark(6, s);
 }
 
@@ -254,6 +291,32 @@ std::unique_ptr<Bases> bases_upload(Context *ctx, const uint64_t *xy, const uint
     return b;
 }
 
+// Build the table of multiples for every shard (one-time, at upload).  c = 0: choose from the shard size
+// and `budget_bytes` of device memory per shard.  Returns the window size used (0 = not applicable).
+template <class F>
+unsigned bases_precompute(Context *ctx, Bases *bases, unsigned c, size_t budget_bytes) {
+    unsigned used = 0;
+    for (auto &sh : bases->shards) {
+        if (sh.n == 0) continue;
+        Device &dv = ctx->devs[sh.dev];
+        set_device(dv.id);
+        size_t point_bytes = 2 * FieldWords<F>::N * 4;
+        unsigned cc = c ? c : choose_precompute_c(sh.n, point_bytes, budget_bytes);
+        if (cc < 8 || cc > 24) throw Error{G16_ERR_INVALID, "precompute window bits must be in [8, 24] and fit the budget"};
+        uint32_t nwin = (256 + cc - 1) / cc;
+        if ((double)nwin * (double)sh.n >= 2147483648.0) throw Error{G16_ERR_INVALID, "precomputed table exceeds 2^31 points"};
+        if (sh.table) { dev_free(sh.table); sh.table = nullptr; sh.pre_c = 0; }
+        uint32_t *table = (uint32_t *)dev_alloc((size_t)nwin * sh.n * point_bytes);
+        try {
+            k_precompute_bases<F>(dv.stream, sh.n, sh.pts, cc, nwin, table);
+            stream_sync(dv.stream);
+        } catch (...) { dev_free(table); throw; }
+        sh.table = table; sh.pre_c = cc;
+        used = cc;
+    }
+    return used;
+}
+
 // Host scalars -> host affine result over all shards of `bases`.
 template <class F>
 void msm_host(Context *ctx, const Bases *bases, const uint64_t *scalars, size_t n, uint64_t *out_xy, uint8_t *out_inf) {
@@ -274,9 +337,9 @@ void msm_host(Context *ctx, const Bases *bases, const uint64_t *scalars, size_t 
         copy_h2d(d_sc, scalars + lo * 4, cnt * 32, dv.stream);
         uint32_t *d_out = dv.ws.out.as<uint32_t>(PW + AW);
         if (nsh == 1) {
-            msm_run<F>(dv, sh.pts, d_sc, cnt, true, ctx->c_override, nullptr, d_out + PW);
+            msm_run<F>(dv, sh, d_sc, cnt, true, ctx->c_override, nullptr, d_out + PW);
         } else {
-            msm_run<F>(dv, sh.pts, d_sc, cnt, true, ctx->c_override, d_out, nullptr);
+            msm_run<F>(dv, sh, d_sc, cnt, true, ctx->c_override, d_out, nullptr);
             copy_d2h(host_partials.data() + k * PW, d_out, PW * 4, dv.stream);
         }
     }

@@ -10,7 +10,10 @@ struct MsmPlan {
     uint32_t c;        // window bits
     uint32_t nwin;     // number of windows = ceil(256 / c)
     uint32_t nb;       // buckets per window = 2^(c-1)
-    uint32_t total;    // nwin * nb
+    uint32_t total;    // bwin * nb
+    uint32_t bwin;     // windows that own a bucket set: nwin, or 1 when the bases carry precomputed
+                       // multiples 2^(c w) P (then every window feeds the same buckets)
+    uint32_t stride;   // precomputed tables: index of (w, i) is w * stride + i; 0 otherwise
 };
 
 template <class P> struct Fp;
@@ -52,6 +55,9 @@ void k_window_combine(stream_t s, const uint32_t *X, const uint32_t *Y, uint32_t
                       uint32_t *out_aff);
 template <class F>
 void k_partial_combine(stream_t s, const uint32_t *partials, uint32_t k, uint32_t *out_xyzz, uint32_t *out_aff);
+// table[w * n + i] = affine(2^(c w) * pts[i]) for w < nwin (w = 0 is a copy)
+template <class F>
+void k_precompute_bases(stream_t s, size_t n, const uint32_t *pts, uint32_t c, uint32_t nwin, uint32_t *table);
 template <class F>
 void k_import_bases(stream_t s, size_t n, const uint32_t *xy, const uint8_t *inf, uint32_t *pts);
 template <class F>

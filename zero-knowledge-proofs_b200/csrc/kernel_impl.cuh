@@ -31,6 +31,10 @@ void k_partial_combine(stream_t s, const uint32_t *partials, uint32_t k, uint32_
     launch<PartialCombine<F>>(1, s, partials, k, out_xyzz, out_aff);
 }
 template <class F>
+void k_precompute_bases(stream_t s, size_t n, const uint32_t *pts, uint32_t c, uint32_t nwin, uint32_t *table) {
+    launch<PrecomputeBases<F>>(n, s, pts, n, c, nwin, table);
+}
+template <class F>
 void k_import_bases(stream_t s, size_t n, const uint32_t *xy, const uint8_t *inf, uint32_t *pts) {
     launch<ImportBases<F>>(n, s, xy, inf, pts);
 }

@@ -61,7 +61,7 @@ struct DigitDecompose {
             uint32_t code = NO_DIGIT;
             if (d != 0) {
                 uint32_t b = (uint32_t)(d < 0 ? -d : d) - 1u;
-                atomic_add_u32(&counts[w * plan.nb + b], 1u);
+                atomic_add_u32(&counts[(plan.bwin == 1 ? 0u : w) * plan.nb + b], 1u);
                 code = b | (d < 0 ? 0x80000000u : 0u);
             }
             codes[(size_t)w * n + i] = code;
@@ -78,8 +78,8 @@ struct ScatterByWindow {
         uint32_t code = codes[t];
         if (code == NO_DIGIT) return;
         uint32_t w = (uint32_t)(t / n), i = (uint32_t)(t % n);
-        uint32_t pos = atomic_add_u32(&cursor[w * plan.nb + (code & 0x7fffffffu)], 1u);
-        entries[pos] = i | (code & 0x80000000u);
+        uint32_t pos = atomic_add_u32(&cursor[(plan.bwin == 1 ? 0u : w) * plan.nb + (code & 0x7fffffffu)], 1u);
+        entries[pos] = (w * plan.stride + i) | (code & 0x80000000u);
     }
 };
 
@@ -156,6 +156,19 @@ G16_HD Affine<F> load_affine(const uint32_t *pts, size_t idx) {
     for (int j = 0; j < F::N; ++j) { dx[j] = src[j]; dy[j] = src[F::N + j]; }
 #endif
     return p;
+}
+
+template <class F>
+G16_HD void store_affine_pt(uint32_t *dst, size_t idx, const Affine<F> &a) {
+    const uint32_t *s = reinterpret_cast<const uint32_t *>(&a);
+    uint32_t *d = dst + idx * (2 * F::N);
+#if G16_DEVICE_CODE
+    uint4 *d4 = reinterpret_cast<uint4 *>(d);
+#pragma unroll
+    for (int j = 0; j < F::N / 2; ++j) d4[j] = make_uint4(s[4 * j], s[4 * j + 1], s[4 * j + 2], s[4 * j + 3]);
+#else
+    for (int j = 0; j < 2 * F::N; ++j) d[j] = s[j];
+#endif
 }
 
 template <class F>
@@ -311,6 +324,45 @@ struct PartialCombine {
             const uint32_t *s = reinterpret_cast<const uint32_t *>(&a);
             for (int j = 0; j < 2 * F::N; ++j) out_aff[j] = s[j];
             out_aff[2 * F::N] = acc.is_inf() ? 1u : 0u;
+        }
+    }
+};
+
+// Precomputed multiples for resident bases: table[w * n + i] = 2^(c w) * P_i as affine points, so that
+// digit w of scalar i adds table[w][i] into ONE shared bucket set -- the Horner fold over windows and
+// (nwin - 1) of the nwin bucket reductions disappear.  One thread per base point: nwin - 1 runs of c
+// doublings, then one shared inversion (Montgomery's trick) to bring all multiples back to affine.
+constexpr uint32_t PRE_MAX_WIN = 32;
+template <class F>
+struct PrecomputeBases {
+    static constexpr int BLOCK = 64;
+    G16_HD static void run(size_t i, const uint32_t *pts, size_t n, uint32_t c, uint32_t nwin, uint32_t *table) {
+        Affine<F> p = load_affine<F>(pts, i);
+        store_affine_pt<F>(table, i, p);
+        if (p.is_inf()) {
+            for (uint32_t w = 1; w < nwin; ++w) store_affine_pt<F>(table, (size_t)w * n + i, p);
+            return;
+        }
+        XYZZ<F> m[PRE_MAX_WIN - 1];
+        F prefix[PRE_MAX_WIN - 1];
+        XYZZ<F> acc = XYZZ<F>::from_affine(p);
+        F run = F::one();
+        for (uint32_t w = 1; w < nwin; ++w) {
+            for (uint32_t s = 0; s < c; ++s) xyzz_dbl(acc);
+            m[w - 1] = acc;
+            prefix[w - 1] = run;            // product of zzz of the earlier multiples
+            run = F::mul(run, acc.zzz);
+        }
+        F inv_all = F::inv(run);
+        for (uint32_t w = nwin - 1; w >= 1; --w) {
+            const XYZZ<F> &q = m[w - 1];
+            F a = F::mul(inv_all, prefix[w - 1]);   // 1 / zzz_w = Z^-3
+            inv_all = F::mul(inv_all, q.zzz);
+            F zi = F::mul(a, q.zz);                 // Z^-1
+            Affine<F> r;
+            r.x = F::mul(q.x, F::sqr(zi));
+            r.y = F::mul(q.y, a);
+            store_affine_pt<F>(table, (size_t)w * n + i, r);
         }
     }
 };

@@ -33,7 +33,7 @@ EXPORTS = [
     "g16_version", "g16_device_count", "g16_ctx_create", "g16_ctx_destroy", "g16_last_error",
     "g16_ctx_set_stream", "g16_ctx_synchronize", "g16_ctx_set_window_bits",
     "g16_g1_bases_upload", "g16_g2_bases_upload", "g16_g1_bases_from_device", "g16_g2_bases_from_device",
-    "g16_bases_free", "g16_bases_len",
+    "g16_bases_free", "g16_bases_len", "g16_bases_precompute",
     "g16_g1_msm", "g16_g2_msm", "g16_g1_msm_oneshot", "g16_g2_msm_oneshot",
     "g16_g1_msm_device", "g16_g2_msm_device",
     "g16_g1_combine_partials_device", "g16_g2_combine_partials_device",
@@ -95,6 +95,7 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
         getattr(lib, f"g16_{g}_combine_partials_device").argtypes = [vp, vp, sz, vp]
         getattr(lib, f"g16_{g}_fixed_base_mul").argtypes = [vp, vp, vp, sz, vp, vp]
         getattr(lib, f"g16_{g}_fixed_base_mul_device").argtypes = [vp, vp, vp, sz, vp]
+    lib.g16_bases_precompute.argtypes = [vp, vp, ctypes.c_uint, sz, ctypes.POINTER(ctypes.c_uint)]
     lib.g16_bases_free.argtypes = [vp]
     lib.g16_bases_free.restype = None
     lib.g16_bases_len.argtypes = [vp]
@@ -126,6 +127,13 @@ class Bases:
 
     def __len__(self):
         return int(self.ctx.lib.g16_bases_len(self.handle))
+
+    def precompute(self, window_bits: int = 0, budget_bytes: int = 0) -> int:
+        """One-time table of multiples 2^(c w) P_i (see g16_bases_precompute); returns c."""
+        used = ctypes.c_uint(0)
+        self.ctx._check(self.ctx.lib.g16_bases_precompute(self.ctx.handle, self.handle, window_bits, budget_bytes,
+                                                          ctypes.byref(used)))
+        return int(used.value)
 
     def free(self):
         if self.handle:
