@@ -128,6 +128,8 @@ typedef struct g16_pk_host {
     size_t num_public;
 } g16_pk_host;
 int g16_pk_upload(g16_ctx *ctx, const g16_pk_host *pk, g16_pk **out);
+/* one-time g16_bases_precompute of the five resident arrays (skipped for arrays of < 256 points) */
+int g16_pk_precompute(g16_ctx *ctx, g16_pk *pk);
 void g16_pk_free(g16_pk *pk);
 /* The group part of Prover::prove (crates/groth16-core/src/lib.rs:164-271).
  *   assignment_fr : num_vars x 4 u64, the already truncated `assignment_fr` of lib.rs:156-161

@@ -374,6 +374,16 @@ int g16_pk_upload(g16_ctx *ctx, const g16_pk_host *pk, g16_pk **out) {
         *out = h.release();
     });
 }
+int g16_pk_precompute(g16_ctx *ctx, g16_pk *pk) {
+    if (!ctx || !pk) return G16_ERR_INVALID;
+    return guarded(ctx, [&] {
+        require(pk->ctx == &ctx->c, "bad pk handle");
+        size_t budget = (size_t)24 << 30;
+        for (Bases *b : {pk->a.get(), pk->b1.get(), pk->ic.get(), pk->h.get()})
+            if (b->n >= 256) bases_precompute<Fq>(&ctx->c, b, 0, budget);
+        if (pk->b2->n >= 256) bases_precompute<Fq2>(&ctx->c, pk->b2.get(), 0, budget);
+    });
+}
 void g16_pk_free(g16_pk *pk) { delete pk; }
 
 static const uint64_t FR_ONE_MONT[4] = {0x00000001fffffffeULL, 0x5884b7fa00034802ULL, 0x998c4fefecbc4ff5ULL,

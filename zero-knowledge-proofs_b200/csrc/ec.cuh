@@ -123,6 +123,23 @@ G16_HD void xyzz_add(XYZZ<F> &acc, const XYZZ<F> &b) {
     acc.zzz = F::mul(F::mul(acc.zzz, b.zzz), ppp);
 }
 
+// Out-of-line full addition for the cold-ish kernels (reduction tree, combine): one copy of the 14
+// multiplications per kernel instead of one per call site; the multiplications inside stay inlined.
+template <class F>
+#if defined(__CUDACC__)
+__host__ __device__ __noinline__
+#else
+inline __attribute__((noinline))
+#endif
+void xyzz_add_call(XYZZ<F> &acc, const XYZZ<F> &b) { xyzz_add(acc, b); }
+template <class F>
+#if defined(__CUDACC__)
+__host__ __device__ __noinline__
+#else
+inline __attribute__((noinline))
+#endif
+void xyzz_dbl_call(XYZZ<F> &acc) { xyzz_dbl(acc); }
+
 // canonical affine point (the form ark's `into_affine` returns); infinity -> (0, 0)
 template <class F>
 G16_HD Affine<F> xyzz_to_affine(const XYZZ<F> &p) {

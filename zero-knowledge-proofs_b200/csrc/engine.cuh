@@ -169,6 +169,7 @@ inline unsigned choose_precompute_c(size_t n, size_t point_bytes, size_t budget)
 }
 
 constexpr uint32_t REDUCE_LOG_L = 5;
+constexpr size_t TILE_LEVEL_MAX = 1u << 18;   // levels with at most this many entries run block-cooperatively
 
 // One MSM on one device, asynchronous on dv.stream.
 //   pts        : packed affine bases on this device (n points)
@@ -233,16 +234,28 @@ void msm_run(Device &dv, const BasesShard &sh, const uint32_t *d_scalars, size_t
     uint32_t n_in = plan.nb, shift = 0;
     int flip = 0;
     while (n_in > 1) {
-        // group size 2^log_l: 32 while there is plenty of parallelism (least total work), smaller near the
-        // top of the tree where the level is latency bound (one thread walks 2^log_l entries serially)
-        uint32_t log_l = REDUCE_LOG_L;
-        while (log_l > 2 && (size_t)plan.bwin * ((n_in + (1u << log_l) - 1) >> log_l) < 16384) --log_l;
-        uint32_t L = 1u << log_l;
-        uint32_t n_out = (n_in + L - 1) / L;
-        uint32_t *Xo = ws.red[flip].as<uint32_t>((size_t)plan.bwin * n_out * 4 * FieldWords<F>::N);
-        uint32_t *Yo = ws.red[flip + 1].as<uint32_t>((size_t)plan.bwin * n_out * 4 * FieldWords<F>::N);
-        k_reduce_level<F>(s, (size_t)plan.bwin * n_out, X, Y, n_in, n_out, L, shift, Xo, Yo);
-        X = Xo; Y = Yo;
+        uint32_t n_out, log_l;
+        if ((size_t)plan.bwin * n_in > TILE_LEVEL_MAX) {
+            // thread level: every thread walks 32 consecutive entries (least total work)
+            log_l = REDUCE_LOG_L;
+            uint32_t L = 1u << log_l;
+            n_out = (n_in + L - 1) / L;
+            uint32_t *Xo = ws.red[flip].as<uint32_t>((size_t)plan.bwin * n_out * 4 * FieldWords<F>::N);
+            uint32_t *Yo = ws.red[flip + 1].as<uint32_t>((size_t)plan.bwin * n_out * 4 * FieldWords<F>::N);
+            k_reduce_level<F>(s, (size_t)plan.bwin * n_out, X, Y, n_in, n_out, L, shift, Xo, Yo);
+            X = Xo; Y = Yo;
+        } else {
+            // block level: the upper part of the tree is latency bound -> scan + tree inside a block
+            uint32_t tile_max = FieldWords<F>::N == 12 ? 256u : 128u;   // 48 KB of shared memory either way
+            log_l = 1;
+            while ((1u << log_l) < n_in && (1u << log_l) < tile_max) ++log_l;
+            uint32_t T = 1u << log_l;
+            n_out = (n_in + T - 1) / T;
+            uint32_t *Xo = ws.red[flip].as<uint32_t>((size_t)plan.bwin * n_out * 4 * FieldWords<F>::N);
+            uint32_t *Yo = ws.red[flip + 1].as<uint32_t>((size_t)plan.bwin * n_out * 4 * FieldWords<F>::N);
+            k_tile_reduce<F>(s, plan.bwin, X, Y, n_in, n_out, T, shift, Xo, Yo);
+            X = Xo; Y = Yo;
+        }
         n_in = n_out; shift += log_l; flip ^= 2;
     }
     dv.timer.mark(5, s);

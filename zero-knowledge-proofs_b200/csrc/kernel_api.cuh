@@ -50,6 +50,10 @@ void k_chunk_merge(stream_t s, size_t buckets_n, const uint32_t *offsets, const 
 template <class F>
 void k_reduce_level(stream_t s, size_t threads, const uint32_t *X, const uint32_t *Y, uint32_t n_in, uint32_t n_out,
                     uint32_t L, uint32_t shift, uint32_t *Xo, uint32_t *Yo);
+// block-cooperative level: tile = T elements (power of two <= 256), grid (n_out, windows)
+template <class F>
+void k_tile_reduce(stream_t s, uint32_t windows, const uint32_t *X, const uint32_t *Y, uint32_t n_in, uint32_t n_out,
+                   uint32_t T, uint32_t shift, uint32_t *Xo, uint32_t *Yo);
 template <class F>
 void k_window_combine(stream_t s, const uint32_t *X, const uint32_t *Y, uint32_t nwin, uint32_t c, uint32_t *out_xyzz,
                       uint32_t *out_aff);

@@ -22,6 +22,23 @@ void k_reduce_level(stream_t s, size_t threads, const uint32_t *X, const uint32_
     launch<ReduceLevel<F>>(threads, s, X, Y, n_in, n_out, L, shift, Xo, Yo);
 }
 template <class F>
+void k_tile_reduce(stream_t s, uint32_t windows, const uint32_t *X, const uint32_t *Y, uint32_t n_in, uint32_t n_out,
+                   uint32_t T, uint32_t shift, uint32_t *Xo, uint32_t *Yo) {
+#ifndef G16_EMU
+    size_t smem = (size_t)T * 4 * F::N * sizeof(uint32_t);
+    static bool configured = false;
+    if (!configured) {
+        G16_CUDA_CHECK(cudaFuncSetAttribute(tile_reduce_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured = true;
+    }
+    tile_reduce_kernel<F><<<dim3(n_out, windows), T, smem, s>>>(X, Y, n_in, n_out, shift, Xo, Yo);
+    G16_CUDA_CHECK(cudaGetLastError());
+    note_launch();
+#else
+    launch<TileReduceSerial<F>>((size_t)windows * n_out, s, X, Y, n_in, n_out, T, shift, Xo, Yo);
+#endif
+}
+template <class F>
 void k_window_combine(stream_t s, const uint32_t *X, const uint32_t *Y, uint32_t nwin, uint32_t c, uint32_t *out_xyzz,
                       uint32_t *out_aff) {
     launch<WindowCombine<F>>(1, s, X, Y, nwin, c, out_xyzz, out_aff);

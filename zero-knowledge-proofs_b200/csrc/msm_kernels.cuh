@@ -236,7 +236,7 @@ struct ChunkMerge {
         uint32_t first = item_start[g];
         for (uint32_t j = 0; j < nch; ++j) {
             XYZZ<F> p = load_xyzz<F>(chunk_out, first + j);
-            xyzz_add(acc, p);
+            xyzz_add_call(acc, p);
         }
         store_xyzz<F>(buckets, g, acc);
     }
@@ -261,20 +261,119 @@ struct ReduceLevel {
         XYZZ<F> running = XYZZ<F>::inf(), acc = XYZZ<F>::inf();
         for (uint32_t i = hi; i-- > lo + 1;) {
             XYZZ<F> x = load_xyzz<F>(X, base + i);
-            xyzz_add(running, x);
-            xyzz_add(acc, running);
+            xyzz_add_call(running, x);
+            xyzz_add_call(acc, running);
         }
         {
             XYZZ<F> x0 = load_xyzz<F>(X, base + lo);
-            xyzz_add(running, x0);
+            xyzz_add_call(running, x0);
         }
-        for (uint32_t s = 0; s < shift; ++s) xyzz_dbl(acc);
+        for (uint32_t s = 0; s < shift; ++s) xyzz_dbl_call(acc);
         if (Y) {
             for (uint32_t i = lo; i < hi; ++i) {
                 XYZZ<F> y = load_xyzz<F>(Y, base + i);
-                xyzz_add(acc, y);
+                xyzz_add_call(acc, y);
             }
         }
+        store_xyzz<F>(Xo, (size_t)w * n_out + g, running);
+        store_xyzz<F>(Yo, (size_t)w * n_out + g, acc);
+    }
+};
+
+// Block-cooperative level of the same reduction for the upper, latency-bound part of the tree: one
+// thread per element, TILE elements per block.  A suffix scan gives P_j = sum_{k >= j} X_k, so that
+//   X' = P_0   and   sum_j j X_j = sum_{j >= 1} P_j   (one tree reduction),
+// i.e. 2 log2(TILE) dependent additions per level instead of 3 TILE for a serial walk.
+// Shared memory holds one XYZZ per thread, stored word-major (conflict free).
+#if !defined(G16_EMU) && defined(__CUDACC__)
+template <class F>
+__device__ __forceinline__ void tile_put(uint32_t *sm, int T, int j, const XYZZ<F> &p) {
+    const uint32_t *s = reinterpret_cast<const uint32_t *>(&p);
+#pragma unroll
+    for (int k = 0; k < 4 * F::N; ++k) sm[k * T + j] = s[k];
+}
+template <class F>
+__device__ __forceinline__ XYZZ<F> tile_get(const uint32_t *sm, int T, int j) {
+    XYZZ<F> p;
+    uint32_t *d = reinterpret_cast<uint32_t *>(&p);
+#pragma unroll
+    for (int k = 0; k < 4 * F::N; ++k) d[k] = sm[k * T + j];
+    return p;
+}
+template <class F>
+__global__ void __launch_bounds__(256) tile_reduce_kernel(const uint32_t *X, const uint32_t *Y, uint32_t n_in, uint32_t n_out, uint32_t shift,
+                                   uint32_t *Xo, uint32_t *Yo) {
+    extern __shared__ uint32_t sm[];
+    const int T = blockDim.x, j = threadIdx.x;
+    const uint32_t w = blockIdx.y, g = blockIdx.x;
+    const size_t base = (size_t)w * n_in;
+    const uint32_t i = g * T + j;
+    XYZZ<F> p = XYZZ<F>::inf(), y = XYZZ<F>::inf();
+    if (i < n_in) {
+        p = load_xyzz<F>(X, base + i);
+        if (Y) y = load_xyzz<F>(Y, base + i);
+    }
+    // suffix scan (Hillis-Steele)
+    for (int d = 1; d < T; d <<= 1) {
+        tile_put<F>(sm, T, j, p);
+        __syncthreads();
+        if (j + d < T) {
+            XYZZ<F> q = tile_get<F>(sm, T, j + d);
+            xyzz_add_call(p, q);
+        }
+        __syncthreads();
+    }
+    if (j == 0) store_xyzz<F>(Xo, (size_t)w * n_out + g, p);
+    // R = sum_{j >= 1} P_j
+    XYZZ<F> v = j >= 1 ? p : XYZZ<F>::inf();
+    for (int d = T >> 1; d >= 1; d >>= 1) {
+        tile_put<F>(sm, T, j, v);
+        __syncthreads();
+        if (j < d) {
+            XYZZ<F> q = tile_get<F>(sm, T, j + d);
+            xyzz_add_call(v, q);
+        }
+        __syncthreads();
+    }
+    // sum of the already weighted partials
+    if (Y) {
+        for (int d = T >> 1; d >= 1; d >>= 1) {
+            tile_put<F>(sm, T, j, y);
+            __syncthreads();
+            if (j < d) {
+                XYZZ<F> q = tile_get<F>(sm, T, j + d);
+                xyzz_add_call(y, q);
+            }
+            __syncthreads();
+        }
+    }
+    if (j == 0) {
+        for (uint32_t s = 0; s < shift; ++s) xyzz_dbl_call(v);
+        xyzz_add_call(v, y);
+        store_xyzz<F>(Yo, (size_t)w * n_out + g, v);
+    }
+}
+#endif
+// Serial statement of one tile (host emulation build; also documents what the kernel above computes).
+template <class F>
+struct TileReduceSerial {
+    static constexpr int BLOCK = 32;
+    G16_HD static void run(size_t t, const uint32_t *X, const uint32_t *Y, uint32_t n_in, uint32_t n_out, uint32_t T,
+                           uint32_t shift, uint32_t *Xo, uint32_t *Yo) {
+        uint32_t w = (uint32_t)(t / n_out), g = (uint32_t)(t % n_out);
+        size_t base = (size_t)w * n_in;
+        uint32_t lo = g * T, hi = lo + T < n_in ? lo + T : n_in;
+        XYZZ<F> running = XYZZ<F>::inf(), acc = XYZZ<F>::inf(), ysum = XYZZ<F>::inf();
+        for (uint32_t i = hi; i-- > lo + 1;) {
+            XYZZ<F> x = load_xyzz<F>(X, base + i);
+            xyzz_add_call(running, x);
+            xyzz_add_call(acc, running);
+        }
+        XYZZ<F> x0 = load_xyzz<F>(X, base + lo);
+        xyzz_add_call(running, x0);
+        for (uint32_t s = 0; s < shift; ++s) xyzz_dbl_call(acc);
+        if (Y) for (uint32_t i = lo; i < hi; ++i) { XYZZ<F> y = load_xyzz<F>(Y, base + i); xyzz_add_call(ysum, y); }
+        xyzz_add_call(acc, ysum);
         store_xyzz<F>(Xo, (size_t)w * n_out + g, running);
         store_xyzz<F>(Yo, (size_t)w * n_out + g, acc);
     }
@@ -290,12 +389,12 @@ struct WindowCombine {
                            uint32_t *out_xyzz, uint32_t *out_aff) {
         XYZZ<F> acc = XYZZ<F>::inf();
         for (uint32_t w = nwin; w-- > 0;) {
-            for (uint32_t s = 0; s < c; ++s) xyzz_dbl(acc);
+            for (uint32_t s = 0; s < c; ++s) xyzz_dbl_call(acc);
             XYZZ<F> x = load_xyzz<F>(X, w);
-            xyzz_add(acc, x);
+            xyzz_add_call(acc, x);
             if (Y) {
                 XYZZ<F> y = load_xyzz<F>(Y, w);
-                xyzz_add(acc, y);
+                xyzz_add_call(acc, y);
             }
         }
         if (out_xyzz) store_xyzz<F>(out_xyzz, 0, acc);
@@ -316,7 +415,7 @@ struct PartialCombine {
         XYZZ<F> acc = XYZZ<F>::inf();
         for (uint32_t i = 0; i < k; ++i) {
             XYZZ<F> p = load_xyzz<F>(partials, i);
-            xyzz_add(acc, p);
+            xyzz_add_call(acc, p);
         }
         if (out_xyzz) store_xyzz<F>(out_xyzz, 0, acc);
         if (out_aff) {
