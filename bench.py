@@ -227,13 +227,11 @@ def main():
     gathered = torch.zeros(48 * world, dtype=torch.int32, device=dev)
     out = torch.zeros(25, dtype=torch.int32, device=dev)
 
+    from groth16_cuda.dist import msm_sharded
+
     def step_device(scalars_ptr):
-        if world == 1:
-            ctx.msm_device("g1", bases, scalars_ptr, n_loc, out.data_ptr(), 0)
-        else:
-            ctx.msm_device("g1", bases, scalars_ptr, n_loc, 0, partial.data_ptr())
-            dist.all_gather_into_tensor(gathered, partial)
-            ctx.combine_partials_device("g1", gathered.data_ptr(), world, out.data_ptr())
+        # local pipeline -> (N > 1: NCCL all-gather of the 192-byte partials -> fold) -> affine result
+        msm_sharded(ctx, "g1", bases, scalars_ptr, n_loc, partial, gathered, out, world)
 
     def barrier():
         torch.cuda.synchronize()

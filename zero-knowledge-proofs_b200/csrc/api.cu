@@ -109,6 +109,16 @@ void g16_ctx_destroy(g16_ctx *ctx) {
 #endif
         d.ws.release();
         d.timer.destroy();
+        for (auto &l : d.extra) {
+#ifndef G16_EMU
+            if (l->stream) cudaStreamSynchronize(l->stream);
+#endif
+            l->ws.release();
+            l->timer.destroy();
+#ifndef G16_EMU
+            if (l->own_stream && l->stream) cudaStreamDestroy(l->stream);
+#endif
+        }
 #ifndef G16_EMU
         if (d.own_stream && d.stream) cudaStreamDestroy(d.stream);
 #endif
@@ -135,7 +145,11 @@ int g16_ctx_set_stream(g16_ctx *ctx, void *cuda_stream) {
 int g16_ctx_synchronize(g16_ctx *ctx) {
     if (!ctx) return G16_ERR_INVALID;
     return guarded(ctx, [&] {
-        for (auto &d : ctx->c.devs) { set_device(d.id); stream_sync(d.stream); }
+        for (auto &d : ctx->c.devs) {
+            set_device(d.id);
+            stream_sync(d.stream);
+            for (auto &l : d.extra) stream_sync(l->stream);
+        }
     });
 }
 
@@ -406,40 +420,48 @@ int g16_prove(g16_ctx *ctx, const g16_pk *pk, const uint64_t *assignment_fr, siz
         auto put = [](std::vector<uint64_t> &v, const uint64_t *x) { v.insert(v.end(), x, x + 4); };
         uint8_t inf_a = 0, inf_b = 0, inf_b1 = 0, inf_h = 1, inf_c = 0;
 
+        // The four independent MSMs are launched on four lanes (streams) before any of them is awaited,
+        // so the latency-bound tails of one overlap the bucket accumulation of the others.
         // pi_A = alpha + sum w_i a_i + r delta                                        (lib.rs:164-179)
         size_t na = std::min(num_vars, pk->a_len);
-        std::vector<uint64_t> sc;
-        sc.reserve((na + 2) * 4);
-        put(sc, FR_ONE_MONT); put(sc, r);
-        sc.insert(sc.end(), assignment_fr, assignment_fr + na * 4);
-        msm_host<Fq>(c, pk->a.get(), sc.data(), na + 2, a_xy, &inf_a);
+        std::vector<uint64_t> sc_a, sc_b, sc_b1;
+        sc_a.reserve((na + 2) * 4);
+        put(sc_a, FR_ONE_MONT); put(sc_a, r);
+        sc_a.insert(sc_a.end(), assignment_fr, assignment_fr + na * 4);
+        msm_launch<Fq>(c, pk->a.get(), sc_a.data(), na + 2, 0);
 
         // pi_B = beta + sum w_i b_i + s delta  (G2)                                   (lib.rs:182-197)
         size_t nb2 = std::min(num_vars, pk->b2_len);
-        sc.clear();
-        put(sc, FR_ONE_MONT); put(sc, s);
-        sc.insert(sc.end(), assignment_fr, assignment_fr + nb2 * 4);
-        msm_host<Fq2>(c, pk->b2.get(), sc.data(), nb2 + 2, b_xy, &inf_b);
+        put(sc_b, FR_ONE_MONT); put(sc_b, s);
+        sc_b.insert(sc_b.end(), assignment_fr, assignment_fr + nb2 * 4);
+        msm_launch<Fq2>(c, pk->b2.get(), sc_b.data(), nb2 + 2, 1);
 
         // [H(s)]_1                                                                      (lib.rs:211-221)
         uint64_t h_xy[12] = {0};
         size_t nh = h_coeffs ? std::min(num_h, pk->h_len) : 0;
-        if (nh) msm_host<Fq>(c, pk->h.get(), h_coeffs, nh, h_xy, &inf_h);
+        if (nh) msm_launch<Fq>(c, pk->h.get(), h_coeffs, nh, 2);
 
         // pi_B' = beta_1 + sum w_i b_g1[i]                                              (lib.rs:246-255)
         size_t nb1 = std::min(num_vars, pk->b1_len);
         uint64_t b1_xy[12];
-        sc.clear();
-        put(sc, FR_ONE_MONT);
-        sc.insert(sc.end(), assignment_fr, assignment_fr + nb1 * 4);
-        msm_host<Fq>(c, pk->b1.get(), sc.data(), nb1 + 1, b1_xy, &inf_b1);
+        put(sc_b1, FR_ONE_MONT);
+        sc_b1.insert(sc_b1.end(), assignment_fr, assignment_fr + nb1 * 4);
+        msm_launch<Fq>(c, pk->b1.get(), sc_b1.data(), nb1 + 1, 3);
 
-        // pi_C = sum_{private} w_i ic_i + H + s pi_A + r pi_B'                          (lib.rs:224-265)
+        // main part of pi_C (private-input terms) on lane 0 behind pi_A                 (lib.rs:224-233)
         size_t first_priv = pk->num_public + 1;
         size_t nic = num_vars > first_priv ? std::min(num_vars - first_priv, pk->ic_len) : 0;
         uint64_t cm_xy[12] = {0};
         uint8_t inf_cm = 1;
-        if (nic) msm_host<Fq>(c, pk->ic.get(), assignment_fr + first_priv * 4, nic, cm_xy, &inf_cm);
+
+        msm_finish<Fq>(c, pk->a.get(), 0, a_xy, &inf_a);
+        if (nic) msm_launch<Fq>(c, pk->ic.get(), assignment_fr + first_priv * 4, nic, 0);
+        if (nh) msm_finish<Fq>(c, pk->h.get(), 2, h_xy, &inf_h);
+        msm_finish<Fq>(c, pk->b1.get(), 3, b1_xy, &inf_b1);
+        if (nic) msm_finish<Fq>(c, pk->ic.get(), 0, cm_xy, &inf_cm);
+        std::vector<uint64_t> sc;
+
+        // pi_C = sum_{private} w_i ic_i + H + s pi_A + r pi_B'                          (lib.rs:224-265)
         uint64_t adhoc_xy[4 * 12];
         uint8_t adhoc_inf[4] = {inf_cm, inf_h, inf_a, inf_b1};
         memcpy(adhoc_xy, cm_xy, 96); memcpy(adhoc_xy + 12, h_xy, 96); memcpy(adhoc_xy + 24, a_xy, 96); memcpy(adhoc_xy + 36, b1_xy, 96);
@@ -449,6 +471,7 @@ int g16_prove(g16_ctx *ctx, const g16_pk *pk, const uint64_t *assignment_fr, siz
             std::unique_ptr<Bases> adhoc = bases_upload<Fq>(c, adhoc_xy, adhoc_inf, 4);
             msm_host<Fq>(c, adhoc.get(), sc.data(), 4, c_xy, &inf_c);
         }
+        msm_finish<Fq2>(c, pk->b2.get(), 1, b_xy, &inf_b);   // the G2 MSM ran beside everything above
         if (a_inf) *a_inf = inf_a;
         if (b_inf) *b_inf = inf_b;
         if (c_inf) *c_inf = inf_c;

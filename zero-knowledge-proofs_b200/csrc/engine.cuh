@@ -73,7 +73,27 @@ struct Device {
     Workspace ws;
     StageTimer timer;
     MsmPlan last_plan{};
+    // extra lanes (own stream + workspace) on the same GPU: lets the latency-bound tail of one MSM
+    // (reduction tree, inversion) overlap the bucket accumulation of another (prove schedule)
+    std::vector<std::unique_ptr<Device>> extra;
+    std::vector<uint32_t> host_partials;   // per-lane staging for the sharded combine
 };
+
+inline void set_device(int id);
+inline Device &lane_of(Device &dv, int k) {
+    if (k == 0) return dv;
+    while ((int)dv.extra.size() < k) {
+        std::unique_ptr<Device> l(new Device);
+        l->id = dv.id;
+#ifndef G16_EMU
+        G16_CUDA_CHECK(cudaSetDevice(dv.id));
+        G16_CUDA_CHECK(cudaStreamCreateWithFlags(&l->stream, cudaStreamNonBlocking));
+        l->own_stream = true;
+#endif
+        dv.extra.push_back(std::move(l));
+    }
+    return *dv.extra[k - 1];
+}
 
 inline void set_device(int id) {
 #ifndef G16_EMU
@@ -330,19 +350,20 @@ unsigned bases_precompute(Context *ctx, Bases *bases, unsigned c, size_t budget_
     return used;
 }
 
-// Host scalars -> host affine result over all shards of `bases`.
+// Host scalars -> host affine result over all shards of `bases`, in two halves so that several MSMs
+// can be in flight on different lanes: msm_launch issues the H2D copies and the whole pipeline of every
+// shard asynchronously, msm_finish waits, folds the per-shard partials on device 0 and returns the point.
 template <class F>
-void msm_host(Context *ctx, const Bases *bases, const uint64_t *scalars, size_t n, uint64_t *out_xy, uint8_t *out_inf) {
+void msm_launch(Context *ctx, const Bases *bases, const uint64_t *scalars, size_t n, int lane) {
     if (bases->group != GroupOf<F>::id) throw Error{G16_ERR_INVALID, "bases belong to the other group"};
     if (n > bases->n) throw Error{G16_ERR_LENGTH, "more scalars than bases (ark: Err(min_len))"};
     constexpr size_t PW = 4 * FieldWords<F>::N, AW = 2 * FieldWords<F>::N + 1;
-    Device &d0 = ctx->devs[0];
     size_t nsh = bases->shards.size();
-    // launch every shard (asynchronous), then gather the partials on device 0
-    std::vector<uint32_t> host_partials(nsh * PW);
+    Device &l0 = lane_of(ctx->devs[0], lane);
+    l0.host_partials.assign(nsh * PW, 0u);
     for (size_t k = 0; k < nsh; ++k) {
         const BasesShard &sh = bases->shards[k];
-        Device &dv = ctx->devs[sh.dev];
+        Device &dv = lane_of(ctx->devs[sh.dev], lane);
         set_device(dv.id);
         size_t lo = std::min(sh.begin, n), hi = std::min(sh.begin + sh.n, n);
         size_t cnt = hi - lo;
@@ -353,25 +374,42 @@ void msm_host(Context *ctx, const Bases *bases, const uint64_t *scalars, size_t 
             msm_run<F>(dv, sh, d_sc, cnt, true, ctx->c_override, nullptr, d_out + PW);
         } else {
             msm_run<F>(dv, sh, d_sc, cnt, true, ctx->c_override, d_out, nullptr);
-            copy_d2h(host_partials.data() + k * PW, d_out, PW * 4, dv.stream);
+            copy_d2h(l0.host_partials.data() + k * PW, d_out, PW * 4, dv.stream);
         }
     }
+}
+
+template <class F>
+void msm_finish(Context *ctx, const Bases *bases, int lane, uint64_t *out_xy, uint8_t *out_inf) {
+    constexpr size_t PW = 4 * FieldWords<F>::N, AW = 2 * FieldWords<F>::N + 1;
+    size_t nsh = bases->shards.size();
+    Device &d0 = lane_of(ctx->devs[0], lane);
     uint32_t aff[AW];
     set_device(d0.id);
     if (nsh == 1) {
         copy_d2h(aff, (uint32_t *)d0.ws.out.p + PW, AW * 4, d0.stream);
         stream_sync(d0.stream);
     } else {
-        for (size_t k = 0; k < nsh; ++k) { set_device(ctx->devs[bases->shards[k].dev].id); stream_sync(ctx->devs[bases->shards[k].dev].stream); }
+        for (size_t k = 0; k < nsh; ++k) {
+            Device &dv = lane_of(ctx->devs[bases->shards[k].dev], lane);
+            set_device(dv.id);
+            stream_sync(dv.stream);
+        }
         set_device(d0.id);
         uint32_t *d_part = d0.ws.partials.as<uint32_t>(nsh * PW + AW);
-        copy_h2d(d_part, host_partials.data(), nsh * PW * 4, d0.stream);
+        copy_h2d(d_part, d0.host_partials.data(), nsh * PW * 4, d0.stream);
         k_partial_combine<F>(d0.stream, d_part, (uint32_t)nsh, nullptr, d_part + nsh * PW);
         copy_d2h(aff, d_part + nsh * PW, AW * 4, d0.stream);
         stream_sync(d0.stream);
     }
     memcpy(out_xy, aff, (AW - 1) * 4);
     if (out_inf) *out_inf = (uint8_t)aff[AW - 1];
+}
+
+template <class F>
+void msm_host(Context *ctx, const Bases *bases, const uint64_t *scalars, size_t n, uint64_t *out_xy, uint8_t *out_inf) {
+    msm_launch<F>(ctx, bases, scalars, n, 0);
+    msm_finish<F>(ctx, bases, 0, out_xy, out_inf);
 }
 
 // ---------------------------------------------------------------------------------------
