@@ -54,7 +54,8 @@ def parse_args():
     ap.add_argument("--no-precompute", action="store_true",
                     help="skip the one-time table of multiples 2^(c w) P for the resident bases")
     ap.add_argument("--precompute-bits", type=int, default=0)
-    ap.add_argument("--cpu-sample-log-n", type=int, default=17)
+    ap.add_argument("--cpu-sample-log-n", type=int, default=None,
+                    help="log2 of the bounded CPU sample (default 17 for cpu_baseline, 19 for --impl reference)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -130,7 +131,7 @@ def run_reference(args):
     import bls12_381 as bls
     import cpu_oracle as oracle
     oracle.build()
-    log_s = args.cpu_sample_log_n
+    log_s = min(args.cpu_sample_log_n or 19, args.log_n)
     n = 1 << log_s
     threads = oracle.max_threads()
     g1 = np.array(bls.g1_to_mont(bls.G1_GEN)[0], dtype=np.uint64)
@@ -300,7 +301,7 @@ def main():
     # ---- CPU baseline on a bounded sample (rank 0, N = 1 only) -------------------------------------
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        m = min(n_loc, 1 << args.cpu_sample_log_n)
+        m = min(n_loc, 1 << (args.cpu_sample_log_n or 17))
         pts_h = d_pts[:m].cpu().numpy().view(np.uint32).view(np.uint64).reshape(m, 12)
         inf_h = (~pts_h.any(axis=1)).astype(np.uint8)
         sc_h = np.ascontiguousarray(s_all[:m])

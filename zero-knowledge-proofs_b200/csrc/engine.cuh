@@ -13,11 +13,11 @@ enum Group { GROUP_G1 = 1, GROUP_G2 = 2 };
 template <class F> struct GroupOf { static constexpr int id = FieldWords<F>::group; };
 
 struct Workspace {
-    DevBuf scalars, counts, codes, bins, items, item_start, chunk_out, cursor, entries, buckets, red[4], scan_tmp, out, partials, staging;
+    DevBuf scalars, counts, codes, ranks, bins, items, item_start, chunk_out, cursor, entries, buckets, red[4], scan_tmp, out, partials, staging;
     DevBuf fb_base, fb_powers, fb_table[3], fb_out, fb_flags;
     std::vector<uint32_t> fb_table_key[3];  // base limbs the cached table was built for
     void release() {
-        scalars.release(); counts.release(); codes.release(); bins.release(); items.release(); item_start.release(); chunk_out.release(); cursor.release(); entries.release(); buckets.release();
+        scalars.release(); counts.release(); codes.release(); ranks.release(); bins.release(); items.release(); item_start.release(); chunk_out.release(); cursor.release(); entries.release(); buckets.release();
         for (auto &r : red) r.release();
         scan_tmp.release(); out.release(); partials.release(); staging.release();
         fb_base.release(); fb_powers.release(); fb_out.release(); fb_flags.release();
@@ -217,7 +217,9 @@ void msm_run(Device &dv, const BasesShard &sh, const uint32_t *d_scalars, size_t
     uint32_t *counts = ws.counts.as<uint32_t>(total + 1);
     dev_memset(counts, 0, (total + 1) * sizeof(uint32_t), s);
     uint32_t *codes = ws.codes.as<uint32_t>(max_entries);
-    k_digit_decompose(s, n, d_scalars, mont, plan, counts, codes);
+    static const bool ranked = getenv("G16_ATOMIC_SCATTER") == nullptr;   // default: rank-based scatter
+    uint32_t *ranks = ranked ? ws.ranks.as<uint32_t>(max_entries) : nullptr;
+    k_digit_decompose(s, n, d_scalars, mont, plan, counts, codes, ranks);
     dv.timer.mark(1, s);
     // 2. bucket offsets (exclusive scan; offsets[total] = number of entries) and the work-item list
     //    (bucket slices ordered by length, longest first)
@@ -238,10 +240,14 @@ void msm_run(Device &dv, const BasesShard &sh, const uint32_t *d_scalars, size_t
     k_item_scatter(s, total, offsets, bin_cursor, items, item_start);
     dv.timer.mark(2, s);
     // 3. counting-sort scatter of (point index, sign) into bucket order, one window at a time
-    uint32_t *cursor = ws.cursor.as<uint32_t>(total);
-    copy_d2d(cursor, offsets, total * sizeof(uint32_t), s);
     uint32_t *entries = ws.entries.as<uint32_t>(max_entries);
-    k_scatter_by_window(s, n, codes, plan, cursor, entries);
+    if (ranked) {
+        k_scatter_ranked(s, n, codes, ranks, plan, offsets, entries);
+    } else {
+        uint32_t *cursor = ws.cursor.as<uint32_t>(total);
+        copy_d2d(cursor, offsets, total * sizeof(uint32_t), s);
+        k_scatter_by_window(s, n, codes, plan, cursor, entries);
+    }
     dv.timer.mark(3, s);
     // 4. bucket accumulation (the hot kernel) + fold of split buckets
     uint32_t *buckets = ws.buckets.as<uint32_t>(total * 4 * FieldWords<F>::N);
@@ -335,7 +341,8 @@ unsigned bases_precompute(Context *ctx, Bases *bases, unsigned c, size_t budget_
         set_device(dv.id);
         size_t point_bytes = 2 * FieldWords<F>::N * 4;
         unsigned cc = c ? c : choose_precompute_c(sh.n, point_bytes, budget_bytes);
-        if (cc < 8 || cc > 24) throw Error{G16_ERR_INVALID, "precompute window bits must be in [8, 24] and fit the budget"};
+        if (!c && cc == 0) continue;   // nothing fits the budget: this shard stays plain
+        if (cc < 8 || cc > 24) throw Error{G16_ERR_INVALID, "precompute window bits must be in [8, 24]"};
         uint32_t nwin = (256 + cc - 1) / cc;
         if ((double)nwin * (double)sh.n >= 2147483648.0) throw Error{G16_ERR_INVALID, "precomputed table exceeds 2^31 points"};
         if (sh.table) { dev_free(sh.table); sh.table = nullptr; sh.pre_c = 0; }

@@ -7,8 +7,12 @@ static std::atomic<unsigned long long> g_launches{0};
 void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 unsigned long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
 void k_digit_decompose(stream_t s, size_t n, const uint32_t *scalars, bool mont, MsmPlan plan, uint32_t *counts,
-                        uint32_t *codes) {
-    launch<DigitDecompose>(n, s, scalars, mont, plan, n, counts, codes);
+                        uint32_t *codes, uint32_t *ranks) {
+    launch<DigitDecompose>(n, s, scalars, mont, plan, n, counts, codes, ranks);
+}
+void k_scatter_ranked(stream_t s, size_t n, const uint32_t *codes, const uint32_t *ranks, MsmPlan plan,
+                      const uint32_t *offsets, uint32_t *entries) {
+    launch<ScatterRanked>(n * plan.nwin, s, codes, ranks, plan, n, offsets, entries);
 }
 void k_scatter_by_window(stream_t s, size_t n, const uint32_t *codes, MsmPlan plan, uint32_t *cursor, uint32_t *entries) {
     launch<ScatterByWindow>(n * plan.nwin, s, codes, plan, n, cursor, entries);

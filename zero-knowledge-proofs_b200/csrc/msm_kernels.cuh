@@ -52,7 +52,7 @@ constexpr uint32_t NO_DIGIT = 0xffffffffu;
 struct DigitDecompose {
     static constexpr int BLOCK = 256;
     G16_HD static void run(size_t i, const uint32_t *scalars, bool mont, MsmPlan plan, size_t n, uint32_t *counts,
-                           uint32_t *codes) {
+                           uint32_t *codes, uint32_t *ranks) {
         uint32_t k[8];
         load_scalar(scalars, i, mont, k);
         DigitIter it(k, plan.c);
@@ -61,7 +61,10 @@ struct DigitDecompose {
             uint32_t code = NO_DIGIT;
             if (d != 0) {
                 uint32_t b = (uint32_t)(d < 0 ? -d : d) - 1u;
-                atomic_add_u32(&counts[(plan.bwin == 1 ? 0u : w) * plan.nb + b], 1u);
+                // the histogram atomic also hands out this digit's rank inside its bucket, so the scatter
+                // pass needs no second round of atomics (position = bucket offset + rank)
+                uint32_t rank = atomic_add_u32(&counts[(plan.bwin == 1 ? 0u : w) * plan.nb + b], 1u);
+                if (ranks) ranks[(size_t)w * n + i] = rank;
                 code = b | (d < 0 ? 0x80000000u : 0u);
             }
             codes[(size_t)w * n + i] = code;
@@ -79,6 +82,19 @@ struct ScatterByWindow {
         if (code == NO_DIGIT) return;
         uint32_t w = (uint32_t)(t / n), i = (uint32_t)(t % n);
         uint32_t pos = atomic_add_u32(&cursor[(plan.bwin == 1 ? 0u : w) * plan.nb + (code & 0x7fffffffu)], 1u);
+        entries[pos] = (w * plan.stride + i) | (code & 0x80000000u);
+    }
+};
+
+// Same scatter with the ranks recorded by DigitDecompose: no atomics, position = offset + rank.
+struct ScatterRanked {
+    static constexpr int BLOCK = 256;
+    G16_HD static void run(size_t t, const uint32_t *codes, const uint32_t *ranks, MsmPlan plan, size_t n,
+                           const uint32_t *offsets, uint32_t *entries) {
+        uint32_t code = codes[t];
+        if (code == NO_DIGIT) return;
+        uint32_t w = (uint32_t)(t / n), i = (uint32_t)(t % n);
+        uint32_t pos = offsets[(plan.bwin == 1 ? 0u : w) * plan.nb + (code & 0x7fffffffu)] + ranks[t];
         entries[pos] = (w * plan.stride + i) | (code & 0x80000000u);
     }
 };
