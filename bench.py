@@ -275,8 +275,14 @@ def main():
 
     # ---- end to end through the C ABI with host scalars ("e2e") -------------------------------------
     def step_e2e():
-        d_s.copy_(h_s, non_blocking=True)             # H2D of this step's scalars from pinned memory
-        step_device(d_s.data_ptr())
+        # the reference-facing C-ABI call with HOST buffers: the library copies this step's scalars from
+        # pinned host memory (chunked, overlapped with the pipeline) and leaves the result on the device
+        if world == 1:
+            ctx.msm_async("g1", bases, h_s.data_ptr(), n_loc, out.data_ptr(), 0)
+        else:
+            ctx.msm_async("g1", bases, h_s.data_ptr(), n_loc, 0, partial.data_ptr())
+            dist.all_gather_into_tensor(gathered, partial)
+            ctx.combine_partials_device("g1", gathered.data_ptr(), world, out.data_ptr())
         return out.cpu()                               # D2H of the affine result (synchronises)
 
     for _ in range(max(1, args.warmup // 2)):

@@ -99,6 +99,13 @@ int g16_g1_msm_device(g16_ctx *ctx, const g16_bases *bases, const void *dev_scal
                       void *dev_out_partial);
 int g16_g2_msm_device(g16_ctx *ctx, const g16_bases *bases, const void *dev_scalars, size_t n, void *dev_out_affine,
                       void *dev_out_partial);
+/* HOST scalars in, results on the device, asynchronous on the ctx stream (single-device ctx, unsharded
+ * bases).  The H2D copy is pipelined against the computation in chunks for large n.  `scalars` must stay
+ * valid until the stream has been synchronised (g16_ctx_synchronize or the caller's own stream sync). */
+int g16_g1_msm_async(g16_ctx *ctx, const g16_bases *bases, const uint64_t *scalars, size_t n, void *dev_out_affine,
+                     void *dev_out_partial);
+int g16_g2_msm_async(g16_ctx *ctx, const g16_bases *bases, const uint64_t *scalars, size_t n, void *dev_out_affine,
+                     void *dev_out_partial);
 int g16_g1_combine_partials_device(g16_ctx *ctx, const void *dev_partials, size_t k, void *dev_out_affine);
 int g16_g2_combine_partials_device(g16_ctx *ctx, const void *dev_partials, size_t k, void *dev_out_affine);
 
@@ -147,6 +154,8 @@ unsigned long long g16_launch_count(void);
  * [digit count, offset scan, scatter, bucket accumulate, bucket reduce, window combine];
  * plan = {window bits, windows, buckets per window} */
 int g16_ctx_enable_stage_timing(g16_ctx *ctx, int on);
+/* host-scalar MSMs with at least min_scalars scalars per device are pipelined in 4 chunks (default 2^22) */
+int g16_ctx_set_chunk_min(g16_ctx *ctx, size_t min_scalars);
 int g16_ctx_last_stage_ms(g16_ctx *ctx, float ms[6], unsigned plan[3]);
 /* element-wise Fq ops on the device: op 0 mul, 1 add, 2 sub, 3 inverse(a), 4 square(a), 5 negate(a);
  * a, b, out: n x 6 u64 Montgomery (b may be NULL for unary ops) */

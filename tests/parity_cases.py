@@ -173,3 +173,31 @@ def check_debug_group_add(ctx, oracle, gens):
         for i in range(n):
             exp, einf = msm(np.stack([p[i], q[i]]), np.array([pinf[i], qinf[i]], dtype=np.uint8), one)
             assert einf == oinf[i] and (exp == out[i]).all(), (g, i)
+
+
+def check_chunked_host_path(ctx, oracle, gens, n, seed):
+    """Host-scalar MSMs above the chunk threshold are cut into 4 index ranges that run on separate lanes
+    (H2D of chunk k+1 overlaps the pipeline of chunk k) and are folded on the device: same group element,
+    for plain and for precomputed resident bases, G1 and G2, including a prefix of the bases."""
+    import ctypes
+    ctx.lib.g16_ctx_set_chunk_min.argtypes = [ctypes.c_void_p, ctypes.c_size_t]
+    assert ctx.lib.g16_ctx_set_chunk_min(ctx.handle, 64) == 0
+    try:
+        for group, m in (("g1", n), ("g2", max(70, n // 4))):
+            pts, inf, sc = helpers.adversarial(oracle, gens, group, seed, m)
+            msm = oracle.g1_msm if group == "g1" else oracle.g2_msm
+            exp, einf = msm(pts, inf, sc, threads=oracle.max_threads())
+            bases = ctx.g1_bases_upload(pts, inf) if group == "g1" else ctx.g2_bases_upload(pts, inf)
+            f = ctx.g1_msm if group == "g1" else ctx.g2_msm
+            out, oinf = f(bases, sc)
+            assert oinf == einf and (out == exp).all(), (group, "plain")
+            bases.precompute(9)
+            out, oinf = f(bases, sc)
+            assert oinf == einf and (out == exp).all(), (group, "precomputed")
+            k = m - 7
+            exp, einf = msm(pts[:k], inf[:k], sc[:k])
+            out, oinf = f(bases, sc[:k])
+            assert oinf == einf and (out == exp).all(), (group, "prefix")
+            bases.free()
+    finally:
+        ctx.lib.g16_ctx_set_chunk_min(ctx.handle, 1 << 22)

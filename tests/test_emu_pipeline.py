@@ -31,3 +31,7 @@ def test_emu_adversarial_and_skewed(emu_ctx, oracle, gens):
     pc.check_adversarial(emu_ctx, oracle, gens, "g2", 60, 6)
     pc.check_skewed_scalars(emu_ctx, oracle, gens, 200, 7)
     pc.check_skewed_scalars(emu_ctx, oracle, gens, 1500, 8)   # > ITEM_MAX entries per bucket: split + merge path
+
+
+def test_emu_chunked_host_path(emu_ctx, oracle, gens):
+    pc.check_chunked_host_path(emu_ctx, oracle, gens, 400, 21)

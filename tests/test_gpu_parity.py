@@ -162,3 +162,7 @@ def test_large_msm_by_discrete_log(gpu_ctx, oracle, gens, log_n):
     exp2, _ = oracle.g1_fixed_base_mul(gens[0], np.array([bls.fr_to_mont(e2)], dtype=np.uint64))
     assert (host2[:24].view(np.uint64) == exp2[0]).all()
     bases.free()
+
+
+def test_chunked_host_path(gpu_ctx, oracle, gens):
+    pc.check_chunked_host_path(gpu_ctx, oracle, gens, 5000, 21)

@@ -289,6 +289,29 @@ int g16_g2_msm_device(g16_ctx *ctx, const g16_bases *bases, const void *dev_scal
 
 extern "C++" {
 template <class F>
+static int msm_h2d_impl(g16_ctx *ctx, const g16_bases *bases, const uint64_t *scalars, size_t n, void *dev_out_affine,
+                        void *dev_out_partial) {
+    if (!ctx) return G16_ERR_INVALID;
+    return guarded(ctx, [&] {
+        single_device(ctx);
+        require(bases && bases->b->ctx == &ctx->c, "bad bases handle");
+        require(scalars || n == 0, "scalars is NULL");
+        require(dev_out_affine || dev_out_partial, "no output");
+        msm_launch<F>(&ctx->c, bases->b.get(), scalars, n, 0, (uint32_t *)dev_out_partial, (uint32_t *)dev_out_affine);
+    });
+}
+}  // extern "C++"
+int g16_g1_msm_async(g16_ctx *ctx, const g16_bases *bases, const uint64_t *scalars, size_t n, void *dev_out_affine,
+                     void *dev_out_partial) {
+    return msm_h2d_impl<Fq>(ctx, bases, scalars, n, dev_out_affine, dev_out_partial);
+}
+int g16_g2_msm_async(g16_ctx *ctx, const g16_bases *bases, const uint64_t *scalars, size_t n, void *dev_out_affine,
+                     void *dev_out_partial) {
+    return msm_h2d_impl<Fq2>(ctx, bases, scalars, n, dev_out_affine, dev_out_partial);
+}
+
+extern "C++" {
+template <class F>
 static int combine_impl(g16_ctx *ctx, const void *dev_partials, size_t k, void *dev_out_affine) {
     if (!ctx) return G16_ERR_INVALID;
     return guarded(ctx, [&] {
@@ -481,6 +504,11 @@ int g16_prove(g16_ctx *ctx, const g16_pk *pk, const uint64_t *assignment_fr, siz
 // ---- test hooks --------------------------------------------------------------------------------
 unsigned long long g16_launch_count(void) { return launch_count(); }
 
+int g16_ctx_set_chunk_min(g16_ctx *ctx, size_t min_scalars) {
+    if (!ctx || min_scalars < 8) return G16_ERR_INVALID;
+    ctx->c.chunk_min = min_scalars;
+    return G16_OK;
+}
 int g16_ctx_enable_stage_timing(g16_ctx *ctx, int on) {
     if (!ctx) return G16_ERR_INVALID;
     for (auto &d : ctx->c.devs) { d.timer.enabled = on != 0; d.timer.valid = false; }

@@ -103,10 +103,15 @@ inline void set_device(int id) {
 #endif
 }
 
+constexpr size_t CHUNK_MIN_SCALARS = 1u << 22;   // host-scalar MSMs at least this long are pipelined in chunks
+constexpr size_t H2D_CHUNKS = 4;
+constexpr int CHUNK_LANE_BASE = 8;                // lanes 8.. are reserved for chunk pipelines
+
 struct Context {
     std::vector<Device> devs;
     std::string err;
     unsigned c_override = 0;
+    size_t chunk_min = CHUNK_MIN_SCALARS;   // host-scalar MSMs at least this long are pipelined in chunks
 };
 
 struct BasesShard {
@@ -158,6 +163,7 @@ inline MsmPlan make_plan(size_t n, unsigned c_override, size_t point_words) {
     p.total = p.nwin * p.nb;
     p.bwin = p.nwin;
     p.stride = 0;
+    p.offset = 0;
     return p;
 }
 
@@ -170,6 +176,7 @@ inline MsmPlan make_shared_plan(unsigned c, size_t stride) {
     p.total = p.nb;
     p.bwin = 1;
     p.stride = (uint32_t)stride;
+    p.offset = 0;
     return p;
 }
 
@@ -197,7 +204,8 @@ constexpr size_t TILE_LEVEL_MAX = 1u << 18;   // levels with at most this many e
 //   d_out_xyzz : 4*FieldWords<F>::N words (may be null), d_out_aff : 2*FieldWords<F>::N + 1 words (may be null)
 template <class F>
 void msm_run(Device &dv, const BasesShard &sh, const uint32_t *d_scalars, size_t n, bool mont, unsigned c_override,
-             uint32_t *d_out_xyzz, uint32_t *d_out_aff) {
+             uint32_t *d_out_xyzz, uint32_t *d_out_aff, size_t first = 0) {
+    // bases [first, first + n) of the shard
     const uint32_t *pts = sh.table ? sh.table : sh.pts;
     stream_t s = dv.stream;
     Workspace &ws = dv.ws;
@@ -207,6 +215,7 @@ void msm_run(Device &dv, const BasesShard &sh, const uint32_t *d_scalars, size_t
     }
     if (n >= (1ull << 31)) throw Error{G16_ERR_INVALID, "MSM length must be < 2^31"};
     MsmPlan plan = sh.table ? make_shared_plan(sh.pre_c, sh.n) : make_plan(n, c_override, 2 * FieldWords<F>::N);
+    plan.offset = (uint32_t)first;
     size_t total = plan.total;
     if ((double)n * plan.nwin >= 4294967295.0) throw Error{G16_ERR_INVALID, "n * windows exceeds 2^32 entries"};
 
@@ -361,11 +370,14 @@ unsigned bases_precompute(Context *ctx, Bases *bases, unsigned c, size_t budget_
 // can be in flight on different lanes: msm_launch issues the H2D copies and the whole pipeline of every
 // shard asynchronously, msm_finish waits, folds the per-shard partials on device 0 and returns the point.
 template <class F>
-void msm_launch(Context *ctx, const Bases *bases, const uint64_t *scalars, size_t n, int lane) {
+void msm_launch(Context *ctx, const Bases *bases, const uint64_t *scalars, size_t n, int lane,
+                uint32_t *user_xyzz = nullptr, uint32_t *user_aff = nullptr) {
     if (bases->group != GroupOf<F>::id) throw Error{G16_ERR_INVALID, "bases belong to the other group"};
     if (n > bases->n) throw Error{G16_ERR_LENGTH, "more scalars than bases (ark: Err(min_len))"};
     constexpr size_t PW = 4 * FieldWords<F>::N, AW = 2 * FieldWords<F>::N + 1;
     size_t nsh = bases->shards.size();
+    bool user_out = user_xyzz || user_aff;   // results stay on the device (single shard only)
+    if (user_out && nsh != 1) throw Error{G16_ERR_INVALID, "device outputs need unsharded bases"};
     Device &l0 = lane_of(ctx->devs[0], lane);
     l0.host_partials.assign(nsh * PW, 0u);
     for (size_t k = 0; k < nsh; ++k) {
@@ -374,14 +386,36 @@ void msm_launch(Context *ctx, const Bases *bases, const uint64_t *scalars, size_
         set_device(dv.id);
         size_t lo = std::min(sh.begin, n), hi = std::min(sh.begin + sh.n, n);
         size_t cnt = hi - lo;
-        uint32_t *d_sc = dv.ws.scalars.as<uint32_t>(cnt * 8 + 8);
-        copy_h2d(d_sc, scalars + lo * 4, cnt * 32, dv.stream);
         uint32_t *d_out = dv.ws.out.as<uint32_t>(PW + AW);
-        if (nsh == 1) {
-            msm_run<F>(dv, sh, d_sc, cnt, true, ctx->c_override, nullptr, d_out + PW);
+        // Large host-scalar MSMs are cut into chunks that run on separate lanes, so the H2D copy of
+        // chunk k+1 overlaps the pipeline of chunk k; the chunk partials are folded on this lane.
+        size_t chunks = cnt >= ctx->chunk_min ? H2D_CHUNKS : 1;
+        if (chunks == 1) {
+            uint32_t *d_sc = dv.ws.scalars.as<uint32_t>(cnt * 8 + 8);
+            copy_h2d(d_sc, scalars + lo * 4, cnt * 32, dv.stream);
+            if (nsh == 1) {
+                msm_run<F>(dv, sh, d_sc, cnt, true, ctx->c_override, user_xyzz, user_out ? user_aff : d_out + PW, lo - sh.begin);
+            } else {
+                msm_run<F>(dv, sh, d_sc, cnt, true, ctx->c_override, d_out, nullptr, lo - sh.begin);
+                copy_d2h(l0.host_partials.data() + k * PW, d_out, PW * 4, dv.stream);
+            }
         } else {
-            msm_run<F>(dv, sh, d_sc, cnt, true, ctx->c_override, d_out, nullptr);
-            copy_d2h(l0.host_partials.data() + k * PW, d_out, PW * 4, dv.stream);
+            uint32_t *d_parts = dv.ws.partials.as<uint32_t>((chunks + 2) * PW + AW);
+            for (size_t j = 0; j < chunks; ++j) {
+                size_t clo = lo + cnt * j / chunks, chi = lo + cnt * (j + 1) / chunks, ccnt = chi - clo;
+                Device &cl = lane_of(ctx->devs[sh.dev], CHUNK_LANE_BASE + lane * (int)H2D_CHUNKS + (int)j);
+                stream_wait(cl.stream, dv.stream);   // do not overtake earlier work queued on this lane
+                uint32_t *d_sc = cl.ws.scalars.as<uint32_t>(ccnt * 8 + 8);
+                copy_h2d(d_sc, scalars + clo * 4, ccnt * 32, cl.stream);
+                msm_run<F>(cl, sh, d_sc, ccnt, true, ctx->c_override, d_parts + j * PW, nullptr, clo - sh.begin);
+                stream_wait(dv.stream, cl.stream);
+            }
+            if (nsh == 1) {
+                k_partial_combine<F>(dv.stream, d_parts, (uint32_t)chunks, user_xyzz, user_out ? user_aff : d_out + PW);
+            } else {
+                k_partial_combine<F>(dv.stream, d_parts, (uint32_t)chunks, d_out, nullptr);
+                copy_d2h(l0.host_partials.data() + k * PW, d_out, PW * 4, dv.stream);
+            }
         }
     }
 }

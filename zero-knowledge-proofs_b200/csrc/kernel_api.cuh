@@ -14,6 +14,7 @@ struct MsmPlan {
     uint32_t bwin;     // windows that own a bucket set: nwin, or 1 when the bases carry precomputed
                        // multiples 2^(c w) P (then every window feeds the same buckets)
     uint32_t stride;   // precomputed tables: index of (w, i) is w * stride + i; 0 otherwise
+    uint32_t offset;   // index of this call's first base inside the resident array (chunked launches)
 };
 
 template <class P> struct Fp;

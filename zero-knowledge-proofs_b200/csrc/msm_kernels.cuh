@@ -82,7 +82,7 @@ struct ScatterByWindow {
         if (code == NO_DIGIT) return;
         uint32_t w = (uint32_t)(t / n), i = (uint32_t)(t % n);
         uint32_t pos = atomic_add_u32(&cursor[(plan.bwin == 1 ? 0u : w) * plan.nb + (code & 0x7fffffffu)], 1u);
-        entries[pos] = (w * plan.stride + i) | (code & 0x80000000u);
+        entries[pos] = (w * plan.stride + plan.offset + i) | (code & 0x80000000u);
     }
 };
 
@@ -95,7 +95,7 @@ struct ScatterRanked {
         if (code == NO_DIGIT) return;
         uint32_t w = (uint32_t)(t / n), i = (uint32_t)(t % n);
         uint32_t pos = offsets[(plan.bwin == 1 ? 0u : w) * plan.nb + (code & 0x7fffffffu)] + ranks[t];
-        entries[pos] = (w * plan.stride + i) | (code & 0x80000000u);
+        entries[pos] = (w * plan.stride + plan.offset + i) | (code & 0x80000000u);
     }
 };
 

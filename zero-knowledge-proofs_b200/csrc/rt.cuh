@@ -98,6 +98,19 @@ inline void stream_sync(stream_t s) {
 #endif
 }
 
+// lane_b waits (on the device) for everything issued so far on lane_a
+inline void stream_wait(stream_t waiter, stream_t producer) {
+#ifndef G16_EMU
+    cudaEvent_t ev;
+    G16_CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    G16_CUDA_CHECK(cudaEventRecord(ev, producer));
+    G16_CUDA_CHECK(cudaStreamWaitEvent(waiter, ev, 0));
+    G16_CUDA_CHECK(cudaEventDestroy(ev));   // released once the wait has been satisfied
+#else
+    (void)waiter; (void)producer;
+#endif
+}
+
 // atomic add usable from kernel bodies
 G16_HD uint32_t atomic_add_u32(uint32_t *p, uint32_t v) {
 #if G16_DEVICE_CODE

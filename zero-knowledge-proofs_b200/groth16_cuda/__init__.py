@@ -35,7 +35,7 @@ EXPORTS = [
     "g16_g1_bases_upload", "g16_g2_bases_upload", "g16_g1_bases_from_device", "g16_g2_bases_from_device",
     "g16_bases_free", "g16_bases_len", "g16_bases_precompute",
     "g16_g1_msm", "g16_g2_msm", "g16_g1_msm_oneshot", "g16_g2_msm_oneshot",
-    "g16_g1_msm_device", "g16_g2_msm_device",
+    "g16_g1_msm_device", "g16_g2_msm_device", "g16_g1_msm_async", "g16_g2_msm_async",
     "g16_g1_combine_partials_device", "g16_g2_combine_partials_device",
     "g16_g1_fixed_base_mul", "g16_g2_fixed_base_mul",
     "g16_g1_fixed_base_mul_device", "g16_g2_fixed_base_mul_device",
@@ -92,6 +92,7 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
         getattr(lib, f"g16_{g}_msm").argtypes = [vp, vp, vp, sz, vp, vp]
         getattr(lib, f"g16_{g}_msm_oneshot").argtypes = [vp, vp, vp, vp, sz, vp, vp]
         getattr(lib, f"g16_{g}_msm_device").argtypes = [vp, vp, vp, sz, vp, vp]
+        getattr(lib, f"g16_{g}_msm_async").argtypes = [vp, vp, vp, sz, vp, vp]
         getattr(lib, f"g16_{g}_combine_partials_device").argtypes = [vp, vp, sz, vp]
         getattr(lib, f"g16_{g}_fixed_base_mul").argtypes = [vp, vp, vp, sz, vp, vp]
         getattr(lib, f"g16_{g}_fixed_base_mul_device").argtypes = [vp, vp, vp, sz, vp]
@@ -268,6 +269,12 @@ class Context:
     def msm_device(self, g: str, bases: Bases, dev_scalars: int, n: int, dev_out_affine: int = 0, dev_out_partial: int = 0):
         self._check(getattr(self.lib, f"g16_{g}_msm_device")(self.handle, bases.handle, dev_scalars, n,
                                                             dev_out_affine or None, dev_out_partial or None))
+
+    def msm_async(self, g: str, bases: Bases, host_scalars_ptr: int, n: int, dev_out_affine: int = 0,
+                  dev_out_partial: int = 0):
+        """HOST scalars (raw pointer, e.g. a pinned buffer) -> device result, asynchronous on the ctx stream."""
+        self._check(getattr(self.lib, f"g16_{g}_msm_async")(self.handle, bases.handle, host_scalars_ptr, n,
+                                                           dev_out_affine or None, dev_out_partial or None))
 
     def combine_partials_device(self, g: str, dev_partials: int, k: int, dev_out_affine: int):
         self._check(getattr(self.lib, f"g16_{g}_combine_partials_device")(self.handle, dev_partials, k, dev_out_affine))
