@@ -271,8 +271,9 @@ void msm_run(Device &dv, const BasesShard &sh, const uint32_t *d_scalars, size_t
     while (n_in > 1) {
         uint32_t n_out, log_l;
         if ((size_t)plan.bwin * n_in > TILE_LEVEL_MAX) {
-            // thread level: every thread walks 32 consecutive entries (least total work)
-            log_l = REDUCE_LOG_L;
+            // thread level: every thread walks 2^log_l consecutive entries -- 32 when the level is work
+            // bound (millions of buckets), 8 when it is latency bound (a serial walk costs ~14 us per add)
+            log_l = (size_t)plan.bwin * n_in >= ((size_t)1 << 22) ? REDUCE_LOG_L : 3;
             uint32_t L = 1u << log_l;
             n_out = (n_in + L - 1) / L;
             uint32_t *Xo = ws.red[flip].as<uint32_t>((size_t)plan.bwin * n_out * 4 * FieldWords<F>::N);

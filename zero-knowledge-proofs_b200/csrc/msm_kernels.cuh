@@ -277,18 +277,18 @@ struct ReduceLevel {
         XYZZ<F> running = XYZZ<F>::inf(), acc = XYZZ<F>::inf();
         for (uint32_t i = hi; i-- > lo + 1;) {
             XYZZ<F> x = load_xyzz<F>(X, base + i);
-            xyzz_add_call(running, x);
-            xyzz_add_call(acc, running);
+            xyzz_add(running, x);
+            xyzz_add(acc, running);
         }
         {
             XYZZ<F> x0 = load_xyzz<F>(X, base + lo);
-            xyzz_add_call(running, x0);
+            xyzz_add(running, x0);
         }
-        for (uint32_t s = 0; s < shift; ++s) xyzz_dbl_call(acc);
+        for (uint32_t s = 0; s < shift; ++s) xyzz_dbl(acc);
         if (Y) {
             for (uint32_t i = lo; i < hi; ++i) {
                 XYZZ<F> y = load_xyzz<F>(Y, base + i);
-                xyzz_add_call(acc, y);
+                xyzz_add(acc, y);
             }
         }
         store_xyzz<F>(Xo, (size_t)w * n_out + g, running);
