@@ -154,7 +154,9 @@ unsigned long long g16_launch_count(void);
  * [digit count, offset scan, scatter, bucket accumulate, bucket reduce, window combine];
  * plan = {window bits, windows, buckets per window} */
 int g16_ctx_enable_stage_timing(g16_ctx *ctx, int on);
-/* host-scalar MSMs with at least min_scalars scalars per device are pipelined in 4 chunks (default 2^22) */
+/* host-scalar MSMs with at least min_scalars scalars per device are cut into 4 index ranges that run on
+ * separate lanes so the H2D copy of one overlaps the pipeline of another.  Off by default: every chunk pays
+ * its own bucket reduction, which costs more than the copy it hides (measured, profiles/README.md). */
 int g16_ctx_set_chunk_min(g16_ctx *ctx, size_t min_scalars);
 int g16_ctx_last_stage_ms(g16_ctx *ctx, float ms[6], unsigned plan[3]);
 /* element-wise Fq ops on the device: op 0 mul, 1 add, 2 sub, 3 inverse(a), 4 square(a), 5 negate(a);

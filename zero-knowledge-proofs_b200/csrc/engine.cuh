@@ -103,7 +103,7 @@ inline void set_device(int id) {
 #endif
 }
 
-constexpr size_t CHUNK_MIN_SCALARS = 1u << 22;   // host-scalar MSMs at least this long are pipelined in chunks
+constexpr size_t CHUNK_MIN_SCALARS = ~(size_t)0;   // chunked host-scalar pipeline: off by default
 constexpr size_t H2D_CHUNKS = 4;
 constexpr int CHUNK_LANE_BASE = 8;                // lanes 8.. are reserved for chunk pipelines
 
@@ -236,17 +236,22 @@ void msm_run(Device &dv, const BasesShard &sh, const uint32_t *d_scalars, size_t
     k_exclusive_scan(s, counts, counts, total + 1, scan_tmp);
     uint32_t *offsets = counts;
     size_t nbins = k_item_bins();
+    // longest work item: 256 additions when the call is large (a serial walk of 256 is noise), shorter
+    // when it is small and the longest item would set the kernel's duration
+    uint32_t item_max = (uint32_t)std::min<size_t>(k_item_max(), std::max<size_t>(16, max_entries >> 17));
     uint32_t *bins = ws.bins.as<uint32_t>(2 * (nbins + 1));
     uint32_t *bin_cursor = bins + nbins + 1;
     dev_memset(bins, 0, (nbins + 1) * sizeof(uint32_t), s);
-    k_item_count(s, total, offsets, bins);
+    k_item_count(s, total, offsets, item_max, bins);
     k_exclusive_scan(s, bins, bins, nbins + 1, scan_tmp);
     copy_d2d(bin_cursor, bins, (nbins + 1) * sizeof(uint32_t), s);
-    size_t max_split = max_entries / (k_item_max() / 2) + 16;
+    size_t max_split_buckets = max_entries / item_max + 1;           // buckets longer than item_max
+    size_t max_split = 2 * max_split_buckets + 16;                   // chunks they are cut into
     size_t max_items = total + max_split;
     WorkItem *items = (WorkItem *)ws.items.need(max_items * k_item_bytes());
-    uint32_t *item_start = ws.item_start.as<uint32_t>(total);
-    k_item_scatter(s, total, offsets, bin_cursor, items, item_start);
+    uint32_t *split_list = ws.item_start.as<uint32_t>(1 + 3 * max_split_buckets);
+    dev_memset(split_list, 0, sizeof(uint32_t), s);
+    k_item_scatter(s, total, offsets, item_max, bin_cursor, items, split_list);
     dv.timer.mark(2, s);
     // 3. counting-sort scatter of (point index, sign) into bucket order, one window at a time
     uint32_t *entries = ws.entries.as<uint32_t>(max_entries);
@@ -262,7 +267,7 @@ void msm_run(Device &dv, const BasesShard &sh, const uint32_t *d_scalars, size_t
     uint32_t *buckets = ws.buckets.as<uint32_t>(total * 4 * FieldWords<F>::N);
     uint32_t *chunk_out = ws.chunk_out.as<uint32_t>(max_split * 4 * FieldWords<F>::N);
     k_accumulate<F>(s, max_items, pts, entries, items, bins + nbins, buckets, chunk_out);
-    k_chunk_merge<F>(s, total, offsets, item_start, chunk_out, buckets);
+    k_chunk_merge<F>(s, max_split_buckets, split_list, chunk_out, buckets);
     dv.timer.mark(4, s);
     // 5. parallel bucket reduction
     const uint32_t *X = buckets, *Y = nullptr;
@@ -273,7 +278,7 @@ void msm_run(Device &dv, const BasesShard &sh, const uint32_t *d_scalars, size_t
         if ((size_t)plan.bwin * n_in > TILE_LEVEL_MAX) {
             // thread level: every thread walks 2^log_l consecutive entries -- 32 when the level is work
             // bound (millions of buckets), 8 when it is latency bound (a serial walk costs ~14 us per add)
-            log_l = (size_t)plan.bwin * n_in >= ((size_t)1 << 22) ? REDUCE_LOG_L : 3;
+            log_l = REDUCE_LOG_L;
             uint32_t L = 1u << log_l;
             n_out = (n_in + L - 1) / L;
             uint32_t *Xo = ws.red[flip].as<uint32_t>((size_t)plan.bwin * n_out * 4 * FieldWords<F>::N);

@@ -20,12 +20,12 @@ void k_scatter_by_window(stream_t s, size_t n, const uint32_t *codes, MsmPlan pl
 size_t k_item_bins() { return ITEM_BINS; }
 size_t k_item_bytes() { return sizeof(WorkItem); }
 uint32_t k_item_max() { return ITEM_MAX; }
-void k_item_count(stream_t s, size_t buckets, const uint32_t *offsets, uint32_t *bin_counts) {
-    launch<ItemCount>(buckets, s, offsets, bin_counts);
+void k_item_count(stream_t s, size_t buckets, const uint32_t *offsets, uint32_t item_max, uint32_t *bin_counts) {
+    launch<ItemCount>(buckets, s, offsets, item_max, bin_counts);
 }
-void k_item_scatter(stream_t s, size_t buckets, const uint32_t *offsets, uint32_t *bin_cursor, WorkItem *items,
-                    uint32_t *item_start) {
-    launch<ItemScatter>(buckets, s, offsets, bin_cursor, items, item_start);
+void k_item_scatter(stream_t s, size_t buckets, const uint32_t *offsets, uint32_t item_max, uint32_t *bin_cursor,
+                    WorkItem *items, uint32_t *split_list) {
+    launch<ItemScatter>(buckets, s, offsets, item_max, bin_cursor, items, split_list);
 }
 size_t k_scan_tmp_words(size_t n) { return scan_tmp_words(n); }
 void k_exclusive_scan(stream_t s, const uint32_t *in, uint32_t *out, size_t n, uint32_t *tmp) {

@@ -38,9 +38,9 @@ struct WorkItem;
 size_t k_item_bins();
 size_t k_item_bytes();
 uint32_t k_item_max();
-void k_item_count(stream_t s, size_t buckets, const uint32_t *offsets, uint32_t *bin_counts);
-void k_item_scatter(stream_t s, size_t buckets, const uint32_t *offsets, uint32_t *bin_cursor, WorkItem *items,
-                    uint32_t *item_start);
+void k_item_count(stream_t s, size_t buckets, const uint32_t *offsets, uint32_t item_max, uint32_t *bin_counts);
+void k_item_scatter(stream_t s, size_t buckets, const uint32_t *offsets, uint32_t item_max, uint32_t *bin_cursor,
+                    WorkItem *items, uint32_t *split_list);
 size_t k_scan_tmp_words(size_t n);
 void k_exclusive_scan(stream_t s, const uint32_t *in, uint32_t *out, size_t n, uint32_t *tmp);
 
@@ -48,8 +48,7 @@ template <class F>
 void k_accumulate(stream_t s, size_t max_items, const uint32_t *pts, const uint32_t *entries, const WorkItem *work,
                   const uint32_t *n_items, uint32_t *buckets, uint32_t *chunk_out);
 template <class F>
-void k_chunk_merge(stream_t s, size_t buckets_n, const uint32_t *offsets, const uint32_t *item_start,
-                   const uint32_t *chunk_out, uint32_t *buckets);
+void k_chunk_merge(stream_t s, size_t max_split, const uint32_t *split_list, const uint32_t *chunk_out, uint32_t *buckets);
 template <class F>
 void k_reduce_level(stream_t s, size_t threads, const uint32_t *X, const uint32_t *Y, uint32_t n_in, uint32_t n_out,
                     uint32_t L, uint32_t shift, uint32_t *Xo, uint32_t *Yo);

@@ -12,9 +12,16 @@ void k_accumulate(stream_t s, size_t max_items, const uint32_t *pts, const uint3
     launch<BucketAccumulate<F>>(max_items, s, pts, entries, work, n_items, buckets, chunk_out);
 }
 template <class F>
-void k_chunk_merge(stream_t s, size_t buckets_n, const uint32_t *offsets, const uint32_t *item_start,
-                   const uint32_t *chunk_out, uint32_t *buckets) {
-    launch<ChunkMerge<F>>(buckets_n, s, offsets, item_start, chunk_out, buckets);
+void k_chunk_merge(stream_t s, size_t max_split, const uint32_t *split_list, const uint32_t *chunk_out, uint32_t *buckets) {
+#ifndef G16_EMU
+    (void)max_split;
+    size_t smem = (size_t)MERGE_THREADS * 4 * F::N * sizeof(uint32_t);
+    chunk_merge_kernel<F><<<148 * 4, MERGE_THREADS, smem, s>>>(split_list, chunk_out, buckets);
+    G16_CUDA_CHECK(cudaGetLastError());
+    note_launch();
+#else
+    launch<ChunkMergeSerial<F>>(max_split, s, split_list, chunk_out, buckets);
+#endif
 }
 template <class F>
 void k_reduce_level(stream_t s, size_t threads, const uint32_t *X, const uint32_t *Y, uint32_t n_in, uint32_t n_out,

@@ -105,42 +105,45 @@ struct ScatterRanked {
 // skewed scalar distribution (boolean witnesses, repeated values) cannot serialise on one thread.
 // Items are ordered by length, longest first, so the 32 lanes of a warp run loops of (nearly) equal
 // length -- with Poisson-distributed bucket sizes this removes most of the divergence loss.
-constexpr uint32_t ITEM_MAX = 256;
+constexpr uint32_t ITEM_MAX = 256;             // upper limit of the per-call item length
 constexpr uint32_t ITEM_BINS = ITEM_MAX + 2;   // bin 0: chunks of split buckets, bin 1 + (ITEM_MAX - len): whole buckets
 struct WorkItem { uint32_t begin, end, bucket; };  // bucket | SPLIT_FLAG when it is a chunk
 constexpr uint32_t SPLIT_FLAG = 0x80000000u;
 
-G16_HD uint32_t isqrt_ceil(uint32_t v) {
-    uint32_t r = 1;
-    while ((uint64_t)r * r < v) r <<= 1;          // power of two >= sqrt(v): cheap and good enough
-    return r;
-}
-G16_HD void item_shape(uint32_t size, uint32_t &nch, uint32_t &len, uint32_t &bin) {
-    if (size <= ITEM_MAX) { nch = 1; len = size; bin = 1u + (ITEM_MAX - size); return; }
-    uint32_t target = isqrt_ceil(size);
-    if (target < ITEM_MAX) target = ITEM_MAX;
-    nch = (size + target - 1) / target;
+// item_max (<= ITEM_MAX) is chosen per call by the host: long items only when there is so much work that a
+// serial walk of item_max additions is negligible, short ones when the call is small and the longest item
+// would be the critical path (a mixed addition has ~10 us of latency when few warps are resident).
+G16_HD void item_shape(uint32_t size, uint32_t item_max, uint32_t &nch, uint32_t &len, uint32_t &bin) {
+    if (size <= item_max) { nch = 1; len = size; bin = 1u + (ITEM_MAX - size); return; }
+    nch = (size + item_max - 1) / item_max;
     len = (size + nch - 1) / nch;
     bin = 0;
 }
 
 struct ItemCount {
     static constexpr int BLOCK = 256;
-    G16_HD static void run(size_t g, const uint32_t *offsets, uint32_t *bin_counts) {
+    G16_HD static void run(size_t g, const uint32_t *offsets, uint32_t item_max, uint32_t *bin_counts) {
         uint32_t nch, len, bin;
-        item_shape(offsets[g + 1] - offsets[g], nch, len, bin);
+        item_shape(offsets[g + 1] - offsets[g], item_max, nch, len, bin);
         atomic_add_u32(&bin_counts[bin], nch);
     }
 };
 
 struct ItemScatter {
     static constexpr int BLOCK = 256;
-    G16_HD static void run(size_t g, const uint32_t *offsets, uint32_t *bin_cursor, WorkItem *items, uint32_t *item_start) {
+    // split_list[0] counts the split buckets, split_list[1 + k] = {bucket, first item, chunks} (3 words each)
+    G16_HD static void run(size_t g, const uint32_t *offsets, uint32_t item_max, uint32_t *bin_cursor, WorkItem *items,
+                           uint32_t *split_list) {
         uint32_t begin = offsets[g], size = offsets[g + 1] - begin;
         uint32_t nch, len, bin;
-        item_shape(size, nch, len, bin);
+        item_shape(size, item_max, nch, len, bin);
         uint32_t pos = atomic_add_u32(&bin_cursor[bin], nch);
-        item_start[g] = pos;
+        if (nch > 1) {
+            uint32_t k = atomic_add_u32(&split_list[0], 1u);
+            split_list[1 + 3 * k] = (uint32_t)g;
+            split_list[2 + 3 * k] = pos;
+            split_list[3 + 3 * k] = nch;
+        }
         for (uint32_t j = 0; j < nch; ++j) {
             uint32_t b = begin + j * len;
             uint32_t e = b + len < begin + size ? b + len : begin + size;
@@ -239,19 +242,51 @@ struct BucketAccumulate {
     }
 };
 
-// One thread per bucket: buckets that were split get the sum of their chunk partials.
+// Split buckets get the sum of their chunk partials.  GPU: one block per split bucket (grid-stride over
+// the split list): every thread folds a strided subset of the chunks, then a shared-memory tree.
+#if !defined(G16_EMU) && defined(__CUDACC__)
+constexpr int MERGE_THREADS = 64;
 template <class F>
-struct ChunkMerge {
-    static constexpr int BLOCK = 128;
-    G16_HD static void run(size_t g, const uint32_t *offsets, const uint32_t *item_start, const uint32_t *chunk_out,
-                           uint32_t *buckets) {
-        uint32_t nch, len, bin;
-        item_shape(offsets[g + 1] - offsets[g], nch, len, bin);
-        if (nch == 1) return;
+__global__ void __launch_bounds__(MERGE_THREADS) chunk_merge_kernel(const uint32_t *split_list, const uint32_t *chunk_out,
+                                                                    uint32_t *buckets) {
+    extern __shared__ uint32_t sm[];
+    const int T = MERGE_THREADS, j = threadIdx.x;
+    const uint32_t n_split = split_list[0];
+    for (uint32_t k = blockIdx.x; k < n_split; k += gridDim.x) {
+        uint32_t g = split_list[1 + 3 * k], first = split_list[2 + 3 * k], nch = split_list[3 + 3 * k];
         XYZZ<F> acc = XYZZ<F>::inf();
-        uint32_t first = item_start[g];
-        for (uint32_t j = 0; j < nch; ++j) {
-            XYZZ<F> p = load_xyzz<F>(chunk_out, first + j);
+        for (uint32_t c = j; c < nch; c += T) {
+            XYZZ<F> p = load_xyzz<F>(chunk_out, first + c);
+            xyzz_add_call(acc, p);
+        }
+        for (int d = T >> 1; d >= 1; d >>= 1) {
+            const uint32_t *s = reinterpret_cast<const uint32_t *>(&acc);
+#pragma unroll
+            for (int w = 0; w < 4 * F::N; ++w) sm[w * T + j] = s[w];
+            __syncthreads();
+            if (j < d) {
+                XYZZ<F> q;
+                uint32_t *qd = reinterpret_cast<uint32_t *>(&q);
+#pragma unroll
+                for (int w = 0; w < 4 * F::N; ++w) qd[w] = sm[w * T + j + d];
+                xyzz_add_call(acc, q);
+            }
+            __syncthreads();
+        }
+        if (j == 0) store_xyzz<F>(buckets, g, acc);
+    }
+}
+#endif
+// serial statement (host emulation build): one thread per entry of the split list
+template <class F>
+struct ChunkMergeSerial {
+    static constexpr int BLOCK = 64;
+    G16_HD static void run(size_t k, const uint32_t *split_list, const uint32_t *chunk_out, uint32_t *buckets) {
+        if (k >= split_list[0]) return;
+        uint32_t g = split_list[1 + 3 * k], first = split_list[2 + 3 * k], nch = split_list[3 + 3 * k];
+        XYZZ<F> acc = XYZZ<F>::inf();
+        for (uint32_t c = 0; c < nch; ++c) {
+            XYZZ<F> p = load_xyzz<F>(chunk_out, first + c);
             xyzz_add_call(acc, p);
         }
         store_xyzz<F>(buckets, g, acc);
