@@ -20,6 +20,9 @@ struct g16_pk {
 };
 
 static thread_local std::string g_create_error;
+static const uint64_t FR_ONE_MONT[4] = {0x00000001fffffffeULL, 0x5884b7fa00034802ULL, 0x998c4fefecbc4ff5ULL,
+                                        0x1824b159acc5056fULL};
+
 
 template <class Fn>
 static int guarded(g16_ctx *ctx, Fn &&fn) {
@@ -423,8 +426,82 @@ int g16_pk_precompute(g16_ctx *ctx, g16_pk *pk) {
 }
 void g16_pk_free(g16_pk *pk) { delete pk; }
 
-static const uint64_t FR_ONE_MONT[4] = {0x00000001fffffffeULL, 0x5884b7fa00034802ULL, 0x998c4fefecbc4ff5ULL,
-                                        0x1824b159acc5056fULL};
+
+// Single-device fast path of the prove schedule: the assignment is copied to the device once, every MSM
+// gets its (prefix ++ assignment) scalar vector by a device-to-device copy, the five big MSMs run on
+// five lanes, and the ad-hoc terms of pi_C (H, s*pi_A, r*pi_B') are taken from the other lanes' results
+// on the device -- the host waits exactly once, at the end.
+static void prove_single_device(Context *c, const g16_pk *pk, const uint64_t *w, size_t num_vars, const uint64_t *h,
+                                size_t num_h, const uint64_t *r, const uint64_t *s, uint64_t *a_xy, uint8_t *a_inf,
+                                uint64_t *b_xy, uint8_t *b_inf, uint64_t *c_xy, uint8_t *c_inf) {
+    constexpr size_t PW1 = 48, AW1 = 25, PW2 = 96, AW2 = 49;
+    Device &d0 = c->devs[0];
+    set_device(d0.id);
+    Device &LA = lane_of(d0, 0), &LB = lane_of(d0, 1), &LH = lane_of(d0, 2), &LB1 = lane_of(d0, 3), &LC = lane_of(d0, 4);
+    unsigned co = c->c_override;
+    // small host staging block (kept alive until the final synchronisation): prefixes and ad-hoc scalars
+    std::vector<uint64_t> hs(4 * 16);
+    auto put = [&](size_t slot, const uint64_t *x) { memcpy(hs.data() + 4 * slot, x, 32); };
+    put(0, FR_ONE_MONT); put(1, r);          // pi_A prefix   [1, r]
+    put(2, FR_ONE_MONT); put(3, s);          // pi_B prefix   [1, s]
+    put(4, FR_ONE_MONT);                     // pi_B' prefix  [1]
+    put(5, FR_ONE_MONT); put(6, s); put(7, r);   // ad-hoc terms of pi_C: [1 * H, s * pi_A, r * pi_B']
+
+    // assignment: one H2D, shared by four MSMs
+    uint32_t *d_w = LA.ws.prove_w.as<uint32_t>(num_vars * 8 + 8);
+    copy_h2d(d_w, w, num_vars * 32, LA.stream);
+    uint32_t *d_misc = LA.ws.prove_misc.as<uint32_t>(16 * 8 + 3 * 24 + 2 * PW1 + AW1 + 64);
+    uint32_t *d_small = d_misc;                       // 16 scalars
+    uint32_t *d_adhoc_pts = d_misc + 16 * 8;          // 3 packed G1 points
+    uint32_t *d_cparts = d_adhoc_pts + 3 * 24;        // 2 projective partials of pi_C
+    uint32_t *d_c_aff = d_cparts + 2 * PW1;           // pi_C affine
+    copy_h2d(d_small, hs.data(), 16 * 32, LA.stream);
+    for (Device *l : {&LB, &LB1, &LC}) stream_wait(l->stream, LA.stream);
+
+    auto prefixed = [&](Device &L, size_t slot, size_t k, size_t n) {
+        uint32_t *d = L.ws.scalars.as<uint32_t>((k + n) * 8 + 8);
+        copy_d2d(d, d_small + slot * 8, k * 32, L.stream);
+        copy_d2d(d + k * 8, d_w, n * 32, L.stream);
+        return d;
+    };
+    // pi_A (lane 0), pi_B in G2 (lane 1), [H(s)]_1 (lane 2), pi_B' (lane 3), private part of pi_C (lane 4)
+    size_t na = std::min(num_vars, pk->a_len), nb2 = std::min(num_vars, pk->b2_len), nb1 = std::min(num_vars, pk->b1_len);
+    uint32_t *oa = LA.ws.out.as<uint32_t>(PW1 + AW1) + PW1;
+    msm_run<Fq>(LA, pk->a->shards[0], prefixed(LA, 0, 2, na), na + 2, true, co, nullptr, oa);
+    uint32_t *ob = LB.ws.out.as<uint32_t>(PW2 + AW2) + PW2;
+    msm_run<Fq2>(LB, pk->b2->shards[0], prefixed(LB, 2, 2, nb2), nb2 + 2, true, co, nullptr, ob);
+    size_t nh = h ? std::min(num_h, pk->h_len) : 0;
+    uint32_t *oh = LH.ws.out.as<uint32_t>(PW1 + AW1) + PW1;
+    {
+        uint32_t *d_h = LH.ws.scalars.as<uint32_t>(nh * 8 + 8);
+        copy_h2d(d_h, h, nh * 32, LH.stream);
+        msm_run<Fq>(LH, pk->h->shards[0], d_h, nh, true, co, nullptr, oh);     // nh == 0 -> identity
+    }
+    uint32_t *ob1 = LB1.ws.out.as<uint32_t>(PW1 + AW1) + PW1;
+    msm_run<Fq>(LB1, pk->b1->shards[0], prefixed(LB1, 4, 1, nb1), nb1 + 1, true, co, nullptr, ob1);
+    size_t first_priv = pk->num_public + 1;
+    size_t nic = num_vars > first_priv ? std::min(num_vars - first_priv, pk->ic_len) : 0;
+    msm_run<Fq>(LC, pk->ic->shards[0], d_w + first_priv * 8, nic, true, co, d_cparts, nullptr);
+    // ad-hoc part of pi_C on lane 4 once pi_A, H and pi_B' exist (device-side dependency, no host wait)
+    for (Device *l : {&LA, &LH, &LB1}) stream_wait(LC.stream, l->stream);
+    copy_d2d(d_adhoc_pts, oh, 96, LC.stream);
+    copy_d2d(d_adhoc_pts + 24, oa, 96, LC.stream);
+    copy_d2d(d_adhoc_pts + 48, ob1, 96, LC.stream);
+    BasesShard adhoc;
+    adhoc.dev = 0; adhoc.pts = d_adhoc_pts; adhoc.n = 3; adhoc.owned = false;
+    msm_run<Fq>(LC, adhoc, d_small + 5 * 8, 3, true, 0, d_cparts + PW1, nullptr);
+    k_partial_combine<Fq>(LC.stream, d_cparts, 2, nullptr, d_c_aff);
+
+    uint32_t ra[AW1], rb[AW2], rc[AW1];
+    copy_d2h(ra, oa, AW1 * 4, LA.stream);
+    copy_d2h(rb, ob, AW2 * 4, LB.stream);
+    copy_d2h(rc, d_c_aff, AW1 * 4, LC.stream);
+    for (Device *l : {&LA, &LB, &LH, &LB1, &LC}) stream_sync(l->stream);
+    memcpy(a_xy, ra, 96); memcpy(b_xy, rb, 192); memcpy(c_xy, rc, 96);
+    if (a_inf) *a_inf = (uint8_t)ra[24];
+    if (b_inf) *b_inf = (uint8_t)rb[48];
+    if (c_inf) *c_inf = (uint8_t)rc[24];
+}
 
 // The MSM schedule of Prover::prove (crates/groth16-core/src/lib.rs:164-271).  The reference
 // builds fresh (scalar, point) lists with zero scalars filtered out; here the CRS arrays stay
@@ -440,6 +517,10 @@ int g16_prove(g16_ctx *ctx, const g16_pk *pk, const uint64_t *assignment_fr, siz
         require(assignment_fr && r && s && a_xy && b_xy && c_xy, "NULL argument");
         require(num_vars > pk->num_public, "assignment shorter than the public inputs");
         Context *c = &ctx->c;
+        if (c->devs.size() == 1) {
+            prove_single_device(c, pk, assignment_fr, num_vars, h_coeffs, num_h, r, s, a_xy, a_inf, b_xy, b_inf, c_xy, c_inf);
+            return;
+        }
         auto put = [](std::vector<uint64_t> &v, const uint64_t *x) { v.insert(v.end(), x, x + 4); };
         uint8_t inf_a = 0, inf_b = 0, inf_b1 = 0, inf_h = 1, inf_c = 0;
 

@@ -14,13 +14,14 @@ template <class F> struct GroupOf { static constexpr int id = FieldWords<F>::gro
 
 struct Workspace {
     DevBuf scalars, counts, codes, ranks, bins, items, item_start, chunk_out, cursor, entries, buckets, red[4], scan_tmp, out, partials, staging;
+    DevBuf prove_w, prove_misc;
     DevBuf fb_base, fb_powers, fb_table[3], fb_out, fb_flags;
     std::vector<uint32_t> fb_table_key[3];  // base limbs the cached table was built for
     void release() {
         scalars.release(); counts.release(); codes.release(); ranks.release(); bins.release(); items.release(); item_start.release(); chunk_out.release(); cursor.release(); entries.release(); buckets.release();
         for (auto &r : red) r.release();
         scan_tmp.release(); out.release(); partials.release(); staging.release();
-        fb_base.release(); fb_powers.release(); fb_out.release(); fb_flags.release();
+        prove_w.release(); prove_misc.release(); fb_base.release(); fb_powers.release(); fb_out.release(); fb_flags.release();
         for (auto &t : fb_table) t.release();
     }
 };
@@ -147,6 +148,9 @@ inline MsmPlan make_plan(size_t n, unsigned c_override, size_t point_words) {
     unsigned best_c = 1;
     double best = 1e300;
     unsigned lo = 2, hi = 22;
+    // tiny inputs (verifier, ad-hoc prove terms): the cost is the serial fold over the windows, not the
+    // additions -- use few, wide windows
+    if (n < 1024) lo = hi = 8;
     if (c_override) lo = hi = std::min(std::max(c_override, 2u), 24u);
     for (unsigned c = lo; c <= hi; ++c) {
         double nwin = (256 + c - 1) / c;
