@@ -179,7 +179,9 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    if rank == 0:
+    if rank == 0 and not os.path.exists(groth16_cuda.DEFAULT_LIB):
+        # normally prebuilt by __graft_entry__.build(); never rebuilt here when present (the GPU box runs
+        # the library that was built and tested with the snapshot)
         sys.path.insert(0, ROOT)
         import __graft_entry__
         __graft_entry__.build_library()

@@ -21,3 +21,17 @@ for g in g1 g2; do for n in 16 20; do timeout 300 python zero-knowledge-proofs_b
 timeout 300 python zero-knowledge-proofs_b200/tools/bench_stages.py --group g2 --log-n 20 --no-precompute 2>&1 | tail -1
 timeout 300 python zero-knowledge-proofs_b200/tools/bench_stages.py --group g2 --log-n 20 --bits 64 2>&1 | tail -1
 timeout 900 python zero-knowledge-proofs_b200/tools/bench_prove.py --log-n 20 --steps 3 --no-cpu > $OUT/prove20.json 2> $OUT/prove20.err; echo "prove rc=$?"; cat $OUT/prove20.json; tail -3 $OUT/prove20.err
+# per-level timing of the reduction tree at 2^24 (only after the plain run above exited 0)
+python bench.py --log-n 24 --steps 1 --warmup 1 --no-cpu-baseline > $OUT/plain24.log 2>&1 && \
+ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name-base demangled -k regex:"ReduceLevel|tile_reduce|WindowCombine|chunk_merge|ItemScatter|ItemCount|DigitDecompose|Scatter" -c 60 --csv --log-file $OUT/launches24_tail.csv \
+    python bench.py --log-n 24 --steps 1 --warmup 1 --no-cpu-baseline > $OUT/ncu_tail.log 2>&1; echo "ncu tail rc=$?"
+python - <<'PY'
+import csv, re
+try:
+    lines = [l for l in open("gpurun_out/launches24_tail.csv") if not l.startswith("==")]
+    for row in csv.DictReader(lines):
+        m = re.search(r"(ReduceLevel|tile_reduce_kernel|WindowCombine|chunk_merge_kernel|ItemScatter|ItemCount|DigitDecompose|ScatterRanked|ScatterByWindow)", row["Kernel Name"])
+        print(row["ID"], m.group(1) if m else row["Kernel Name"][:30], row["Grid Size"], row["Block Size"], row["Metric Value"], row["Metric Unit"])
+except Exception as e:
+    print("no launch list", e)
+PY

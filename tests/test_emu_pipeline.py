@@ -35,3 +35,8 @@ def test_emu_adversarial_and_skewed(emu_ctx, oracle, gens):
 
 def test_emu_chunked_host_path(emu_ctx, oracle, gens):
     pc.check_chunked_host_path(emu_ctx, oracle, gens, 400, 21)
+
+
+def test_emu_fixed_base_groups(emu_ctx, oracle, gens):
+    # n not a multiple of the inversion group, zero scalars inside a group, another base than the generator
+    pc.check_fixed_base_random(emu_ctx, oracle, gens, 203, 9)

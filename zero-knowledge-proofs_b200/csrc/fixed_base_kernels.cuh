@@ -54,22 +54,47 @@ struct FbTable {
     }
 };
 
-// out[i] = scalar_i * base as a packed affine point ((0,0) = infinity).  One thread per scalar.
+// out[i] = scalar_i * base as a packed affine point ((0,0) = infinity).  One thread per FB_GROUP
+// consecutive scalars: <= 32 mixed additions each, then ONE shared inversion for the group
+// (Montgomery's trick) instead of ark's inversion per element.
+constexpr uint32_t FB_GROUP = 8;
 template <class F>
 struct FbMul {
     static constexpr int BLOCK = 128;
-    G16_HD static void run(size_t i, const uint32_t *scalars, bool mont, const uint32_t *table, uint32_t *out) {
-        uint32_t k[8];
-        load_scalar(scalars, i, mont, k);
-        XYZZ<F> acc = XYZZ<F>::inf();
-        for (uint32_t j = 0; j < FB_WINDOWS; ++j) {
-            uint32_t d = (k[j >> 2] >> ((j & 3u) * 8u)) & 0xffu;
-            if (d) {
-                Affine<F> p = load_affine<F>(table, (size_t)j * FB_ENTRIES + (d - 1u));
-                xyzz_madd(acc, p.x, p.y);
+    G16_HD static void run(size_t t, const uint32_t *scalars, bool mont, const uint32_t *table, size_t n, uint32_t *out) {
+        XYZZ<F> pt[FB_GROUP];
+        F prefix[FB_GROUP];
+        size_t first = t * FB_GROUP;
+        uint32_t cnt = (uint32_t)(n - first < FB_GROUP ? n - first : FB_GROUP);
+        F run = F::one();
+        for (uint32_t e = 0; e < cnt; ++e) {
+            uint32_t k[8];
+            load_scalar(scalars, first + e, mont, k);
+            XYZZ<F> acc = XYZZ<F>::inf();
+            for (uint32_t j = 0; j < FB_WINDOWS; ++j) {
+                uint32_t d = (k[j >> 2] >> ((j & 3u) * 8u)) & 0xffu;
+                if (d) {
+                    Affine<F> p = load_affine<F>(table, (size_t)j * FB_ENTRIES + (d - 1u));
+                    xyzz_madd(acc, p.x, p.y);
+                }
             }
+            pt[e] = acc;
+            prefix[e] = run;                                 // product of the zzz of the earlier finite points
+            if (!acc.is_inf()) run = F::mul(run, acc.zzz);
         }
-        store_affine<F>(out, i, xyzz_to_affine(acc));
+        F inv_all = F::inv(run);
+        for (uint32_t e = cnt; e-- > 0;) {
+            const XYZZ<F> &q = pt[e];
+            Affine<F> r = Affine<F>::inf();
+            if (!q.is_inf()) {
+                F a = F::mul(inv_all, prefix[e]);            // 1 / zzz_e = Z^-3
+                inv_all = F::mul(inv_all, q.zzz);
+                F zi = F::mul(a, q.zz);                      // Z^-1
+                r.x = F::mul(q.x, F::sqr(zi));
+                r.y = F::mul(q.y, a);
+            }
+            store_affine<F>(out, first + e, r);
+        }
     }
 };
 

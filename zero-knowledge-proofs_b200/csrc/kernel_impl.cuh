@@ -76,7 +76,7 @@ void k_fb_table(stream_t s, const uint32_t *powers, uint32_t *table) {
 }
 template <class F>
 void k_fb_mul(stream_t s, size_t n, const uint32_t *scalars, bool mont, const uint32_t *table, uint32_t *out) {
-    launch<FbMul<F>>(n, s, scalars, mont, table, out);
+    launch<FbMul<F>>((n + FB_GROUP - 1) / FB_GROUP, s, scalars, mont, table, n, out);
 }
 
 }  // namespace g16
