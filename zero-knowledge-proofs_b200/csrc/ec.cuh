@@ -140,6 +140,21 @@ inline __attribute__((noinline))
 #endif
 void xyzz_dbl_call(XYZZ<F> &acc) { xyzz_dbl(acc); }
 
+template <class F>
+#if defined(__CUDACC__)
+__host__ __device__ __noinline__
+#else
+inline __attribute__((noinline))
+#endif
+void xyzz_madd_call(XYZZ<F> &acc, const F &x2, const F &y2) { xyzz_madd(acc, x2, y2); }
+template <class F>
+#if defined(__CUDACC__)
+__host__ __device__ __noinline__
+#else
+inline __attribute__((noinline))
+#endif
+F field_inv_call(const F &a) { return F::inv(a); }
+
 // canonical affine point (the form ark's `into_affine` returns); infinity -> (0, 0)
 template <class F>
 G16_HD Affine<F> xyzz_to_affine(const XYZZ<F> &p) {

@@ -75,14 +75,14 @@ struct FbMul {
                 uint32_t d = (k[j >> 2] >> ((j & 3u) * 8u)) & 0xffu;
                 if (d) {
                     Affine<F> p = load_affine<F>(table, (size_t)j * FB_ENTRIES + (d - 1u));
-                    xyzz_madd(acc, p.x, p.y);
+                    xyzz_madd_call(acc, p.x, p.y);
                 }
             }
             pt[e] = acc;
             prefix[e] = run;                                 // product of the zzz of the earlier finite points
             if (!acc.is_inf()) run = F::mul(run, acc.zzz);
         }
-        F inv_all = F::inv(run);
+        F inv_all = field_inv_call(run);
         for (uint32_t e = cnt; e-- > 0;) {
             const XYZZ<F> &q = pt[e];
             Affine<F> r = Affine<F>::inf();
