@@ -242,7 +242,7 @@ void msm_run(Device &dv, const BasesShard &sh, const uint32_t *d_scalars, size_t
     size_t nbins = k_item_bins();
     // longest work item: 256 additions when the call is large (a serial walk of 256 is noise), shorter
     // when it is small and the longest item would set the kernel's duration
-    uint32_t item_max = (uint32_t)std::min<size_t>(k_item_max(), std::max<size_t>(16, max_entries >> 17));
+    uint32_t item_max = (uint32_t)std::min<size_t>(k_item_max(), std::max<size_t>(64, max_entries >> 17));
     uint32_t *bins = ws.bins.as<uint32_t>(2 * (nbins + 1));
     uint32_t *bin_cursor = bins + nbins + 1;
     dev_memset(bins, 0, (nbins + 1) * sizeof(uint32_t), s);
@@ -260,7 +260,15 @@ void msm_run(Device &dv, const BasesShard &sh, const uint32_t *d_scalars, size_t
     // 3. counting-sort scatter of (point index, sign) into bucket order, one window at a time
     uint32_t *entries = ws.entries.as<uint32_t>(max_entries);
     if (ranked) {
-        k_scatter_ranked(s, n, codes, ranks, plan, offsets, entries);
+        // shared bucket set (precomputed bases): a window's writes spread over the whole entries array, so
+        // sweep the bucket range in slabs of <= ~48 MB of entries; per-window bucket sets are local already
+        static const size_t slab_bytes = getenv("G16_SCATTER_SLAB_MB") ? (size_t)atol(getenv("G16_SCATTER_SLAB_MB")) << 20 : (size_t)48 << 20;
+        size_t slabs = (plan.bwin == 1 && slab_bytes) ? (max_entries * 4 + slab_bytes - 1) / slab_bytes : 1;
+        if (slabs > 64) slabs = 64;
+        for (size_t k = 0; k < slabs; ++k) {
+            uint32_t b_lo = (uint32_t)((uint64_t)plan.nb * k / slabs), b_hi = (uint32_t)((uint64_t)plan.nb * (k + 1) / slabs);
+            k_scatter_ranked(s, n, codes, ranks, plan, offsets, b_lo, b_hi, entries);
+        }
     } else {
         uint32_t *cursor = ws.cursor.as<uint32_t>(total);
         copy_d2d(cursor, offsets, total * sizeof(uint32_t), s);

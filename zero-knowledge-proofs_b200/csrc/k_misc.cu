@@ -11,8 +11,8 @@ void k_digit_decompose(stream_t s, size_t n, const uint32_t *scalars, bool mont,
     launch<DigitDecompose>(n, s, scalars, mont, plan, n, counts, codes, ranks);
 }
 void k_scatter_ranked(stream_t s, size_t n, const uint32_t *codes, const uint32_t *ranks, MsmPlan plan,
-                      const uint32_t *offsets, uint32_t *entries) {
-    launch<ScatterRanked>(n * plan.nwin, s, codes, ranks, plan, n, offsets, entries);
+                      const uint32_t *offsets, uint32_t b_lo, uint32_t b_hi, uint32_t *entries) {
+    launch<ScatterRanked>(n * plan.nwin, s, codes, ranks, plan, n, offsets, b_lo, b_hi, entries);
 }
 void k_scatter_by_window(stream_t s, size_t n, const uint32_t *codes, MsmPlan plan, uint32_t *cursor, uint32_t *entries) {
     launch<ScatterByWindow>(n * plan.nwin, s, codes, plan, n, cursor, entries);

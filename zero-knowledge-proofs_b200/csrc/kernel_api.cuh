@@ -31,7 +31,7 @@ template <> struct FieldWords<Fq2> { static constexpr size_t N = 24; static cons
 void k_digit_decompose(stream_t s, size_t n, const uint32_t *scalars, bool mont, MsmPlan plan, uint32_t *counts,
                         uint32_t *codes, uint32_t *ranks);
 void k_scatter_ranked(stream_t s, size_t n, const uint32_t *codes, const uint32_t *ranks, MsmPlan plan,
-                      const uint32_t *offsets, uint32_t *entries);
+                      const uint32_t *offsets, uint32_t b_lo, uint32_t b_hi, uint32_t *entries);
 void k_scatter_by_window(stream_t s, size_t n, const uint32_t *codes, MsmPlan plan, uint32_t *cursor, uint32_t *entries);
 // work items (bucket slices ordered by length); see msm_kernels.cuh
 struct WorkItem;

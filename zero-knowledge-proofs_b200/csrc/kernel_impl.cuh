@@ -14,13 +14,13 @@ void k_accumulate(stream_t s, size_t max_items, const uint32_t *pts, const uint3
 template <class F>
 void k_chunk_merge(stream_t s, size_t max_split, const uint32_t *split_list, const uint32_t *chunk_out, uint32_t *buckets) {
 #ifndef G16_EMU
-    (void)max_split;
+    launch<ChunkMergeSerial<F>>(max_split, s, split_list, chunk_out, MERGE_SERIAL_MAX, buckets);
     size_t smem = (size_t)MERGE_THREADS * 4 * F::N * sizeof(uint32_t);
     chunk_merge_kernel<F><<<148 * 4, MERGE_THREADS, smem, s>>>(split_list, chunk_out, buckets);
     G16_CUDA_CHECK(cudaGetLastError());
     note_launch();
 #else
-    launch<ChunkMergeSerial<F>>(max_split, s, split_list, chunk_out, buckets);
+    launch<ChunkMergeSerial<F>>(max_split, s, split_list, chunk_out, 0xffffffffu, buckets);
 #endif
 }
 template <class F>

@@ -89,10 +89,15 @@ struct ScatterByWindow {
 // Same scatter with the ranks recorded by DigitDecompose: no atomics, position = offset + rank.
 struct ScatterRanked {
     static constexpr int BLOCK = 256;
+    // Only buckets in [b_lo, b_hi) are written by one launch: the engine sweeps the bucket range in slabs
+    // whose slice of `entries` fits in L2, so the scattered 4-byte writes merge there instead of each
+    // dirtying a DRAM sector (the code stream is re-read once per slab -- coalesced and cheap).
     G16_HD static void run(size_t t, const uint32_t *codes, const uint32_t *ranks, MsmPlan plan, size_t n,
-                           const uint32_t *offsets, uint32_t *entries) {
+                           const uint32_t *offsets, uint32_t b_lo, uint32_t b_hi, uint32_t *entries) {
         uint32_t code = codes[t];
         if (code == NO_DIGIT) return;
+        uint32_t b = code & 0x7fffffffu;
+        if (b < b_lo || b >= b_hi) return;
         uint32_t w = (uint32_t)(t / n), i = (uint32_t)(t % n);
         uint32_t pos = offsets[(plan.bwin == 1 ? 0u : w) * plan.nb + (code & 0x7fffffffu)] + ranks[t];
         entries[pos] = (w * plan.stride + plan.offset + i) | (code & 0x80000000u);
@@ -242,6 +247,7 @@ struct BucketAccumulate {
     }
 };
 
+constexpr uint32_t MERGE_SERIAL_MAX = 16;   // buckets with more chunks than this are folded by a whole block
 // Split buckets get the sum of their chunk partials.  GPU: one block per split bucket (grid-stride over
 // the split list): every thread folds a strided subset of the chunks, then a shared-memory tree.
 #if !defined(G16_EMU) && defined(__CUDACC__)
@@ -254,6 +260,7 @@ __global__ void __launch_bounds__(MERGE_THREADS) chunk_merge_kernel(const uint32
     const uint32_t n_split = split_list[0];
     for (uint32_t k = blockIdx.x; k < n_split; k += gridDim.x) {
         uint32_t g = split_list[1 + 3 * k], first = split_list[2 + 3 * k], nch = split_list[3 + 3 * k];
+        if (nch <= MERGE_SERIAL_MAX) continue;   // folded by ChunkMergeSerial (block-uniform branch)
         XYZZ<F> acc = XYZZ<F>::inf();
         for (uint32_t c = j; c < nch; c += T) {
             XYZZ<F> p = load_xyzz<F>(chunk_out, first + c);
@@ -277,13 +284,16 @@ __global__ void __launch_bounds__(MERGE_THREADS) chunk_merge_kernel(const uint32
     }
 }
 #endif
-// serial statement (host emulation build): one thread per entry of the split list
+// one thread per entry of the split list: buckets cut into at most `serial_max` chunks (all of them in the
+// host emulation build, where serial_max = ~0)
 template <class F>
 struct ChunkMergeSerial {
     static constexpr int BLOCK = 64;
-    G16_HD static void run(size_t k, const uint32_t *split_list, const uint32_t *chunk_out, uint32_t *buckets) {
+    G16_HD static void run(size_t k, const uint32_t *split_list, const uint32_t *chunk_out, uint32_t serial_max,
+                           uint32_t *buckets) {
         if (k >= split_list[0]) return;
         uint32_t g = split_list[1 + 3 * k], first = split_list[2 + 3 * k], nch = split_list[3 + 3 * k];
+        if (nch > serial_max) return;
         XYZZ<F> acc = XYZZ<F>::inf();
         for (uint32_t c = 0; c < nch; ++c) {
             XYZZ<F> p = load_xyzz<F>(chunk_out, first + c);
