@@ -262,7 +262,7 @@ void msm_run(Device &dv, const BasesShard &sh, const uint32_t *d_scalars, size_t
     if (ranked) {
         // shared bucket set (precomputed bases): a window's writes spread over the whole entries array, so
         // sweep the bucket range in slabs of <= ~48 MB of entries; per-window bucket sets are local already
-        static const size_t slab_bytes = getenv("G16_SCATTER_SLAB_MB") ? (size_t)atol(getenv("G16_SCATTER_SLAB_MB")) << 20 : (size_t)48 << 20;
+        static const size_t slab_bytes = getenv("G16_SCATTER_SLAB_MB") ? (size_t)atol(getenv("G16_SCATTER_SLAB_MB")) << 20 : (size_t)0;   // off: measured slower (one thread per code per slab)
         size_t slabs = (plan.bwin == 1 && slab_bytes) ? (max_entries * 4 + slab_bytes - 1) / slab_bytes : 1;
         if (slabs > 64) slabs = 64;
         for (size_t k = 0; k < slabs; ++k) {
@@ -299,7 +299,7 @@ void msm_run(Device &dv, const BasesShard &sh, const uint32_t *d_scalars, size_t
             X = Xo; Y = Yo;
         } else {
             // block level: the upper part of the tree is latency bound -> scan + tree inside a block
-            uint32_t tile_max = FieldWords<F>::N == 12 ? 256u : 128u;   // 48 KB of shared memory either way
+            uint32_t tile_max = FieldWords<F>::N == 12 ? 1024u : 512u;   // entries per tile: 256 / 128 threads x 4 entries each
             log_l = 1;
             while ((1u << log_l) < n_in && (1u << log_l) < tile_max) ++log_l;
             uint32_t T = 1u << log_l;

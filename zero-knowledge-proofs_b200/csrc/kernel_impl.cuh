@@ -32,13 +32,15 @@ template <class F>
 void k_tile_reduce(stream_t s, uint32_t windows, const uint32_t *X, const uint32_t *Y, uint32_t n_in, uint32_t n_out,
                    uint32_t T, uint32_t shift, uint32_t *Xo, uint32_t *Yo) {
 #ifndef G16_EMU
-    size_t smem = (size_t)T * 4 * F::N * sizeof(uint32_t);
+    // T = entries per tile = threads * TILE_K
+    uint32_t threads = T / TILE_K < 32 ? 32 : T / TILE_K;
+    size_t smem = (size_t)threads * 4 * F::N * sizeof(uint32_t);
     static bool configured = false;
     if (!configured) {
         G16_CUDA_CHECK(cudaFuncSetAttribute(tile_reduce_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         configured = true;
     }
-    tile_reduce_kernel<F><<<dim3(n_out, windows), T, smem, s>>>(X, Y, n_in, n_out, shift, Xo, Yo);
+    tile_reduce_kernel<F><<<dim3(n_out, windows), threads, smem, s>>>(X, Y, n_in, n_out, T, shift, Xo, Yo);
     G16_CUDA_CHECK(cudaGetLastError());
     note_launch();
 #else

@@ -361,20 +361,28 @@ __device__ __forceinline__ XYZZ<F> tile_get(const uint32_t *sm, int T, int j) {
     for (int k = 0; k < 4 * F::N; ++k) d[k] = sm[k * T + j];
     return p;
 }
+constexpr int TILE_K = 4;   // consecutive entries folded serially by each thread before the block scan
 template <class F>
-__global__ void __launch_bounds__(256) tile_reduce_kernel(const uint32_t *X, const uint32_t *Y, uint32_t n_in, uint32_t n_out, uint32_t shift,
-                                   uint32_t *Xo, uint32_t *Yo) {
+__global__ void __launch_bounds__(256) tile_reduce_kernel(const uint32_t *X, const uint32_t *Y, uint32_t n_in, uint32_t n_out,
+                                                          uint32_t tile_entries, uint32_t shift, uint32_t *Xo, uint32_t *Yo) {
     extern __shared__ uint32_t sm[];
-    const int T = blockDim.x, j = threadIdx.x;
+    const int T = blockDim.x, j = threadIdx.x;     // T * TILE_K >= tile_entries
     const uint32_t w = blockIdx.y, g = blockIdx.x;
     const size_t base = (size_t)w * n_in;
-    const uint32_t i = g * T + j;
-    XYZZ<F> p = XYZZ<F>::inf(), y = XYZZ<F>::inf();
-    if (i < n_in) {
-        p = load_xyzz<F>(X, base + i);
-        if (Y) y = load_xyzz<F>(Y, base + i);
+    const uint32_t local = (uint32_t)j * TILE_K;   // offset of this thread's entries inside the tile
+    const uint32_t first = g * tile_entries + local;
+    // per-thread fold of TILE_K entries: p = their sum, lw = sum_k k * x_k (local weights), y = sum of Y
+    XYZZ<F> p = XYZZ<F>::inf(), lw = XYZZ<F>::inf(), y = XYZZ<F>::inf();
+    for (int k = TILE_K - 1; k >= 0; --k) {
+        uint32_t i = first + k;
+        if (local + k < tile_entries && i < n_in) {
+            XYZZ<F> x = load_xyzz<F>(X, base + i);
+            xyzz_add_call(p, x);
+            if (Y) { XYZZ<F> yy = load_xyzz<F>(Y, base + i); xyzz_add_call(y, yy); }
+        }
+        if (k >= 1) xyzz_add_call(lw, p);      // after the loop: lw = sum_{k>=1} (suffix sum from k) = sum_k k x_k
     }
-    // suffix scan (Hillis-Steele)
+    // suffix scan of the thread sums (Hillis-Steele): p = P_j = sum_{t >= j} S_t
     for (int d = 1; d < T; d <<= 1) {
         tile_put<F>(sm, T, j, p);
         __syncthreads();
@@ -385,8 +393,11 @@ __global__ void __launch_bounds__(256) tile_reduce_kernel(const uint32_t *X, con
         __syncthreads();
     }
     if (j == 0) store_xyzz<F>(Xo, (size_t)w * n_out + g, p);
-    // R = sum_{j >= 1} P_j
+    // sum_i i x_i over the tile = sum_j lw_j + TILE_K * sum_{j >= 1} P_j
     XYZZ<F> v = j >= 1 ? p : XYZZ<F>::inf();
+#pragma unroll 1
+    for (int k = 1; k < TILE_K; k <<= 1) xyzz_dbl_call(v);
+    xyzz_add_call(v, lw);
     for (int d = T >> 1; d >= 1; d >>= 1) {
         tile_put<F>(sm, T, j, v);
         __syncthreads();
