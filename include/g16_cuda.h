@@ -159,7 +159,8 @@ int g16_ctx_enable_stage_timing(g16_ctx *ctx, int on);
  * its own bucket reduction, which costs more than the copy it hides (measured, profiles/README.md). */
 int g16_ctx_set_chunk_min(g16_ctx *ctx, size_t min_scalars);
 int g16_ctx_last_stage_ms(g16_ctx *ctx, float ms[6], unsigned plan[3]);
-/* element-wise Fq ops on the device: op 0 mul, 1 add, 2 sub, 3 inverse(a), 4 square(a), 5 negate(a);
+/* element-wise Fq ops on the device: op 0 mul, 1 add, 2 sub, 3 inverse(a), 4 square(a), 5 negate(a),
+ * 6 square(a) by the dedicated squaring routine (kept for scheduling experiments, see csrc/fp.cuh);
  * a, b, out: n x 6 u64 Montgomery (b may be NULL for unary ops) */
 int g16_debug_fq_op(g16_ctx *ctx, int op, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n);
 /* Fr Montgomery -> canonical (`into_bigint()`), n x 4 u64 */

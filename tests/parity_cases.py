@@ -133,6 +133,8 @@ def check_debug_field(ctx, oracle, n=2000):
         assert (out == ref(a, b)).all(), op
     assert lib.g16_debug_fq_op(ctx.handle, 4, a.ctypes.data, None, out.ctypes.data, a.shape[0]) == 0
     assert (out == oracle.fq_mul(a, a)).all()
+    assert lib.g16_debug_fq_op(ctx.handle, 6, a.ctypes.data, None, out.ctypes.data, a.shape[0]) == 0   # dedicated squaring
+    assert (out == oracle.fq_mul(a, a)).all()
     assert lib.g16_debug_fq_op(ctx.handle, 5, a.ctypes.data, None, out.ctypes.data, a.shape[0]) == 0
     assert (out == oracle.fq_sub(np.zeros_like(a), a)).all()
     nz = a[a.any(axis=1)][:64]

@@ -196,7 +196,13 @@ struct Fp {
     // instead of N^2, then T * R^-1 = redc(T_lo) + T_hi with a product-free CIOS reduction (N^2 wide
     // MADs).  222 instead of 288 IMAD.WIDE for Fq: a squaring costs ~0.78 of a multiplication on the
     // integer-multiply pipe (the extra shifts/adds run on the ALU pipe, which has headroom).
-    G16_MUL_HD static Fp sqr(const Fp &a) {
+    //
+    // MEASURED (B200, profiles/README.md run 7): although it retires 7 % fewer IMAD.WIDE in the bucket
+    // accumulation kernel, the longer dependent structure (product -> doubling -> reduction, ~900 extra ALU
+    // instructions) made that kernel 5 % SLOWER (72.7 -> 76.7 ms at 2^24), so `sqr` below stays `mul(a, a)`
+    // and this routine is kept (and parity-tested in emulation) as `sqr_sos` for future scheduling work.
+    G16_HD static Fp sqr(const Fp &a) { return mul(a, a); }
+    G16_MUL_HD static Fp sqr_sos(const Fp &a) {
         // 1. cross products, kept in two 64-bit aligned accumulators:
         //    ce[k] holds word k (i + j even), co[k] holds word k + 1 (i + j odd)
         uint32_t ce[2 * N], co[2 * N];
