@@ -147,6 +147,16 @@ int g16_prove(g16_ctx *ctx, const g16_pk *pk, const uint64_t *assignment_fr, siz
               const uint64_t *h_coeffs, size_t num_h, const uint64_t r[4], const uint64_t s[4],
               uint64_t a_xy[12], uint8_t *a_inf, uint64_t b_xy[24], uint8_t *b_inf, uint64_t c_xy[12], uint8_t *c_inf);
 
+/* ---- quotient polynomial (the stage that feeds the H MSM) ---------------------------- */
+/* H = (A*B - C) / Z with Z = x^n - 1, from the evaluations of A, B, C on ark-poly's radix-2 domain of size n
+ * (a_evals[i] = <A-row i, assignment>; rows beyond the constraint count are zero).  Same polynomial as
+ * `QAP::compute_quotient_polynomial` (crates/groth16-qap/src/lib.rs:225-271, called at
+ * crates/groth16-core/src/lib.rs:200) for a satisfying assignment.  n must be a power of two; all arrays
+ * are n x 4 u64 Montgomery Fr; h_coeffs receives n coefficients (the top one is zero).  Returns
+ * G16_ERR_INVALID ("Polynomial division failed") when A*B - C does not vanish on the domain. */
+int g16_quotient_h(g16_ctx *ctx, const uint64_t *a_evals, const uint64_t *b_evals, const uint64_t *c_evals, size_t n,
+                   uint64_t *h_coeffs);
+
 /* ---- test hooks (used by tests/ and bench.py only) ------------------------------------------ */
 /* kernels launched by the library since it was loaded */
 unsigned long long g16_launch_count(void);

@@ -96,6 +96,7 @@ def degree(p):
 class QAP:
     def __init__(self, constraints, num_variables):
         """constraints: list of (A, B, C) dicts {variable index: coefficient}."""
+        self.constraints = constraints
         self.num_constraints = len(constraints)
         self.num_variables = num_variables
         self.domain = Domain(max(1, self.num_constraints))     # next_power_of_two(0) == 1
@@ -119,6 +120,16 @@ class QAP:
         b = sum(w * poly_eval(p, point) for w, p in zip(assignment, self.b_polys)) % R
         c = sum(w * poly_eval(p, point) for w, p in zip(assignment, self.c_polys)) % R
         return a, b, c
+
+    def domain_evals(self, assignment):
+        """(a_i, b_i, c_i) = (<A-row i, w>, <B-row i, w>, <C-row i, w>) for the n domain points (zero rows
+        beyond the constraints): the evaluations of A(x) = sum_k w_k A_k(x) etc. on the domain, since
+        A_k is the interpolant of column k (from_r1cs, qap/src/lib.rs:143-170)."""
+        out = []
+        for k in range(3):
+            ev = [sum(coef * assignment[v] for v, coef in row[k].items()) % R for row in self.constraints]
+            out.append(ev + [0] * (self.n - len(ev)))
+        return out
 
     def quotient(self, assignment):
         """compute_quotient_polynomial (qap/src/lib.rs:225-271) incl. ark's divide_by_vanishing_poly."""

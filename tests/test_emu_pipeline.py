@@ -40,3 +40,9 @@ def test_emu_chunked_host_path(emu_ctx, oracle, gens):
 def test_emu_fixed_base_groups(emu_ctx, oracle, gens):
     # n not a multiple of the inversion group, zero scalars inside a group, another base than the generator
     pc.check_fixed_base_random(emu_ctx, oracle, gens, 203, 9)
+
+
+def test_emu_quotient_polynomial(emu_ctx):
+    import quotient_cases as qc
+    qc.check_toy_circuits(emu_ctx)
+    qc.check_random_polynomials(emu_ctx, log_sizes=(0, 1, 2, 3, 5))

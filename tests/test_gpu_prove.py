@@ -22,3 +22,9 @@ def test_config1_proofs_multi_shard_context():
         prove_cases.check_config1(ctx, json.load(open(GOLDEN)))
     finally:
         ctx.close()
+
+
+def test_quotient_polynomial_ntt(gpu_ctx):
+    import quotient_cases as qc
+    qc.check_toy_circuits(gpu_ctx)
+    qc.check_random_polynomials(gpu_ctx, log_sizes=(0, 1, 2, 3, 5, 8, 10))

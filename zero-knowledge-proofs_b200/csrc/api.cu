@@ -582,6 +582,22 @@ int g16_prove(g16_ctx *ctx, const g16_pk *pk, const uint64_t *assignment_fr, siz
     });
 }
 
+// ---- quotient polynomial -----------------------------------------------------------------------
+int g16_quotient_h(g16_ctx *ctx, const uint64_t *a_evals, const uint64_t *b_evals, const uint64_t *c_evals, size_t n,
+                   uint64_t *h_coeffs) {
+    if (!ctx) return G16_ERR_INVALID;
+    return guarded(ctx, [&] {
+        require(a_evals && b_evals && c_evals && h_coeffs, "NULL argument");
+        require(n >= 1 && (n & (n - 1)) == 0 && n <= ((size_t)1 << 28), "domain size must be a power of two <= 2^28");
+        uint32_t log_n = 0;
+        while (((size_t)1 << log_n) < n) ++log_n;
+        Device &dv = ctx->c.devs[0];
+        set_device(dv.id);
+        if (!quotient_host(dv, a_evals, b_evals, c_evals, log_n, h_coeffs))
+            throw Error{G16_ERR_INVALID, "Polynomial division failed: non-zero remainder"};
+    });
+}
+
 // ---- test hooks --------------------------------------------------------------------------------
 unsigned long long g16_launch_count(void) { return launch_count(); }
 

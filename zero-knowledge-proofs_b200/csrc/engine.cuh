@@ -14,14 +14,15 @@ template <class F> struct GroupOf { static constexpr int id = FieldWords<F>::gro
 
 struct Workspace {
     DevBuf scalars, counts, codes, ranks, bins, items, item_start, chunk_out, cursor, entries, buckets, red[4], scan_tmp, out, partials, staging;
-    DevBuf prove_w, prove_misc;
+    DevBuf prove_w, prove_misc, ntt_abc, ntt_tw, ntt_consts, ntt_out;
+    uint32_t ntt_log_n = 0xffffffffu;   // size the cached twiddles / constants were built for (none yet)
     DevBuf fb_base, fb_powers, fb_table[3], fb_out, fb_flags;
     std::vector<uint32_t> fb_table_key[3];  // base limbs the cached table was built for
     void release() {
         scalars.release(); counts.release(); codes.release(); ranks.release(); bins.release(); items.release(); item_start.release(); chunk_out.release(); cursor.release(); entries.release(); buckets.release();
         for (auto &r : red) r.release();
         scan_tmp.release(); out.release(); partials.release(); staging.release();
-        prove_w.release(); prove_misc.release(); fb_base.release(); fb_powers.release(); fb_out.release(); fb_flags.release();
+        prove_w.release(); prove_misc.release(); ntt_abc.release(); ntt_tw.release(); ntt_consts.release(); ntt_out.release(); ntt_log_n = 0xffffffffu; fb_base.release(); fb_powers.release(); fb_out.release(); fb_flags.release();
         for (auto &t : fb_table) t.release();
     }
 };
@@ -469,6 +470,45 @@ template <class F>
 void msm_host(Context *ctx, const Bases *bases, const uint64_t *scalars, size_t n, uint64_t *out_xy, uint8_t *out_inf) {
     msm_launch<F>(ctx, bases, scalars, n, 0);
     msm_finish<F>(ctx, bases, 0, out_xy, out_inf);
+}
+
+// ---------------------------------------------------------------------------------------
+// quotient polynomial H = (A B - C) / Z from domain evaluations (see ntt_kernels.cuh)
+//   evals: host, 3 arrays (a, b, c) of n Fr each (Montgomery), n = 2^log_n;  h: host, n Fr
+// Returns false when A*B - C does not vanish on the domain (the reference's PolynomialDivisionFailed).
+// ---------------------------------------------------------------------------------------
+inline bool quotient_host(Device &dv, const uint64_t *a, const uint64_t *b, const uint64_t *c, uint32_t log_n, uint64_t *h) {
+    Workspace &ws = dv.ws;
+    stream_t s = dv.stream;
+    uint32_t n = 1u << log_n;
+    uint32_t *abc = ws.ntt_abc.as<uint32_t>((size_t)3 * n * 8 + 8);
+    uint32_t *flag = abc + (size_t)3 * n * 8;
+    uint32_t *tw = ws.ntt_tw.as<uint32_t>((size_t)n * 8 + 8);       // tw[n/2] then twi[n/2]
+    uint32_t *twi = tw + (size_t)(n / 2) * 8;
+    uint32_t *consts = ws.ntt_consts.as<uint32_t>(k_ntt_const_words());
+    uint32_t *out = ws.ntt_out.as<uint32_t>((size_t)n * 8);
+    copy_h2d(abc, a, (size_t)n * 32, s);
+    copy_h2d(abc + (size_t)n * 8, b, (size_t)n * 32, s);
+    copy_h2d(abc + (size_t)2 * n * 8, c, (size_t)n * 32, s);
+    dev_memset(flag, 0, 4, s);
+    if (ws.ntt_log_n != log_n) {
+        k_ntt_setup(s, log_n, consts);
+        if (n >= 2) k_ntt_twiddles(s, n, consts, tw, twi);
+        ws.ntt_log_n = log_n;
+    }
+    k_ntt_check_vanish(s, abc, n, flag);
+    // coefficients (bit-reversed), coset shift, values on the coset
+    for (uint32_t half = n / 2; half >= 1; half >>= 1) k_ntt_stage(s, false, 3, abc, twi, n, half);
+    k_ntt_coset_scale(s, 3, abc, consts, n, log_n);
+    for (uint32_t half = 1; half < n; half <<= 1) k_ntt_stage(s, true, 3, abc, tw, n, half);
+    k_ntt_quotient_pointwise(s, abc, consts, n);
+    for (uint32_t half = n / 2; half >= 1; half >>= 1) k_ntt_stage(s, false, 1, abc, twi, n, half);
+    k_ntt_final_scale(s, abc, consts, n, log_n, out);
+    uint32_t bad = 0;
+    copy_d2h(h, out, (size_t)n * 32, s);
+    copy_d2h(&bad, flag, 4, s);
+    stream_sync(s);
+    return bad == 0;
 }
 
 // ---------------------------------------------------------------------------------------

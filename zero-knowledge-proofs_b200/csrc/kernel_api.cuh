@@ -79,6 +79,16 @@ void k_fb_table(stream_t s, const uint32_t *powers, uint32_t *table);
 template <class F>
 void k_fb_mul(stream_t s, size_t n, const uint32_t *scalars, bool mont, const uint32_t *table, uint32_t *out);
 
+// quotient polynomial (Fr NTT), see ntt_kernels.cuh
+size_t k_ntt_const_words();
+void k_ntt_setup(stream_t s, uint32_t log_n, uint32_t *consts);
+void k_ntt_twiddles(stream_t s, uint32_t n, const uint32_t *consts, uint32_t *tw, uint32_t *twi);
+void k_ntt_stage(stream_t s, bool dit, size_t batch, uint32_t *x, const uint32_t *tw, uint32_t n, uint32_t half);
+void k_ntt_coset_scale(stream_t s, size_t batch, uint32_t *x, const uint32_t *consts, uint32_t n, uint32_t log_n);
+void k_ntt_quotient_pointwise(stream_t s, uint32_t *abc, const uint32_t *consts, uint32_t n);
+void k_ntt_final_scale(stream_t s, const uint32_t *x, const uint32_t *consts, uint32_t n, uint32_t log_n, uint32_t *out);
+void k_ntt_check_vanish(stream_t s, const uint32_t *abc, uint32_t n, uint32_t *flag);
+
 // test hooks
 void k_debug_fq_op(stream_t s, size_t n, int op, const uint32_t *a, const uint32_t *b, uint32_t *out);
 void k_debug_fr_from_mont(stream_t s, size_t n, const uint32_t *a, uint32_t *out);

@@ -39,7 +39,7 @@ EXPORTS = [
     "g16_g1_combine_partials_device", "g16_g2_combine_partials_device",
     "g16_g1_fixed_base_mul", "g16_g2_fixed_base_mul",
     "g16_g1_fixed_base_mul_device", "g16_g2_fixed_base_mul_device",
-    "g16_pk_upload", "g16_pk_free", "g16_prove",
+    "g16_pk_upload", "g16_pk_free", "g16_prove", "g16_pk_precompute", "g16_quotient_h",
 ]
 
 
@@ -105,6 +105,7 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.g16_pk_free.argtypes = [vp]
     lib.g16_pk_free.restype = None
     lib.g16_prove.argtypes = [vp, vp, vp, sz, vp, sz, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.g16_quotient_h.argtypes = [vp, vp, vp, vp, sz, vp]
     _libs[path] = lib
     return lib
 
@@ -302,6 +303,17 @@ class Context:
         width = G1_WORDS64 if g == "g1" else G2_WORDS64
         base_xy = _u64(base_xy).reshape(width)
         self._check(getattr(self.lib, f"g16_{g}_fixed_base_mul_device")(self.handle, _ptr(base_xy), dev_scalars, n, dev_out))
+
+    # ---- quotient polynomial
+    def quotient_h(self, a_evals, b_evals, c_evals) -> np.ndarray:
+        """H = (A*B - C) / (x^n - 1) from domain evaluations (QAP::compute_quotient_polynomial); n x 4 u64."""
+        a, b, c = (_u64(x, 4) for x in (a_evals, b_evals, c_evals))
+        n = a.shape[0]
+        if b.shape[0] != n or c.shape[0] != n:
+            raise MSMError(G16_ERR_LENGTH, "evaluation vectors differ in length")
+        h = np.zeros((n, 4), dtype=np.uint64)
+        self._check(self.lib.g16_quotient_h(self.handle, _ptr(a), _ptr(b), _ptr(c), n, _ptr(h)))
+        return h
 
     # ---- prove
     def pk_upload(self, pk: dict) -> ProvingKeyDevice:
