@@ -13,7 +13,7 @@ enum Group { GROUP_G1 = 1, GROUP_G2 = 2 };
 template <class F> struct GroupOf { static constexpr int id = FieldWords<F>::group; };
 
 struct Workspace {
-    DevBuf scalars, counts, codes, ranks, bins, items, item_start, chunk_out, cursor, entries, buckets, red[4], scan_tmp, out, partials, staging;
+    DevBuf scalars, counts, codes, ranks, bins, items, item_start, chunk_out, cursor, entries, buckets, red[6], scan_tmp, out, partials, staging;
     DevBuf prove_w, prove_misc, ntt_abc, ntt_tw, ntt_consts, ntt_out;
     uint32_t ntt_log_n = 0xffffffffu;   // size the cached twiddles / constants were built for (none yet)
     DevBuf fb_base, fb_powers, fb_table[3], fb_out, fb_flags;
@@ -201,7 +201,8 @@ inline unsigned choose_precompute_c(size_t n, size_t point_bytes, size_t budget)
 }
 
 constexpr uint32_t REDUCE_LOG_L = 5;
-constexpr size_t TILE_LEVEL_MAX = 1u << 18;   // levels with at most this many entries run block-cooperatively
+constexpr size_t TILE_LEVEL_MAX = 1u << 16;   // levels with at most this many entries run block-cooperatively
+constexpr size_t THREAD_LEVEL_GROUPS = 1u << 16;   // groups a thread level aims to leave behind
 
 // One MSM on one device, asynchronous on dv.stream.
 //   pts        : packed affine bases on this device (n points)
@@ -282,39 +283,43 @@ void msm_run(Device &dv, const BasesShard &sh, const uint32_t *d_scalars, size_t
     k_accumulate<F>(s, max_items, pts, entries, items, bins + nbins, buckets, chunk_out);
     k_chunk_merge<F>(s, max_split_buckets, split_list, chunk_out, buckets);
     dv.timer.mark(4, s);
-    // 5. parallel bucket reduction
-    const uint32_t *X = buckets, *Y = nullptr;
+    // 5. parallel bucket reduction: thread levels while the level is work bound (every thread walks 2^log_l
+    //    consecutive buckets), then block-cooperative levels (quad additions, scan + tree) for the latency
+    //    bound top of the tree
+    const uint32_t *X = buckets, *Y1 = nullptr, *Y2 = nullptr;
     uint32_t n_in = plan.nb, shift = 0;
     int flip = 0;
+    constexpr size_t PWORDS = 4 * FieldWords<F>::N;
     while (n_in > 1) {
         uint32_t n_out, log_l;
         if ((size_t)plan.bwin * n_in > TILE_LEVEL_MAX) {
-            // thread level: every thread walks 2^log_l consecutive entries -- 32 when the level is work
-            // bound (millions of buckets), 8 when it is latency bound (a serial walk costs ~14 us per add)
-            log_l = REDUCE_LOG_L;
+            // aim at ~2^16 groups: fewer and the serial walk (2 x 2^log_l dependent additions) is latency
+            // bound, more and the tile levels above get more blocks than one wave
+            log_l = 2;
+            while (log_l < REDUCE_LOG_L && ((size_t)plan.bwin * n_in >> log_l) > THREAD_LEVEL_GROUPS) ++log_l;
             uint32_t L = 1u << log_l;
             n_out = (n_in + L - 1) / L;
-            uint32_t *Xo = ws.red[flip].as<uint32_t>((size_t)plan.bwin * n_out * 4 * FieldWords<F>::N);
-            uint32_t *Yo = ws.red[flip + 1].as<uint32_t>((size_t)plan.bwin * n_out * 4 * FieldWords<F>::N);
-            k_reduce_level<F>(s, (size_t)plan.bwin * n_out, X, Y, n_in, n_out, L, shift, Xo, Yo);
-            X = Xo; Y = Yo;
+            uint32_t *Xo = ws.red[flip].as<uint32_t>((size_t)plan.bwin * n_out * PWORDS);
+            uint32_t *Yo = ws.red[flip + 1].as<uint32_t>((size_t)plan.bwin * n_out * PWORDS);
+            k_reduce_level<F>(s, (size_t)plan.bwin * n_out, X, Y1, n_in, n_out, L, shift, Xo, Yo);
+            X = Xo; Y1 = Yo;
         } else {
-            // block level: the upper part of the tree is latency bound -> scan + tree inside a block
-            uint32_t tile_max = FieldWords<F>::N == 12 ? 1024u : 512u;   // entries per tile: 256 / 128 threads x 4 entries each
+            uint32_t tile_max = k_tile_entries();
             log_l = 1;
             while ((1u << log_l) < n_in && (1u << log_l) < tile_max) ++log_l;
             uint32_t T = 1u << log_l;
             n_out = (n_in + T - 1) / T;
-            uint32_t *Xo = ws.red[flip].as<uint32_t>((size_t)plan.bwin * n_out * 4 * FieldWords<F>::N);
-            uint32_t *Yo = ws.red[flip + 1].as<uint32_t>((size_t)plan.bwin * n_out * 4 * FieldWords<F>::N);
-            k_tile_reduce<F>(s, plan.bwin, X, Y, n_in, n_out, T, shift, Xo, Yo);
-            X = Xo; Y = Yo;
+            uint32_t *Xo = ws.red[flip].as<uint32_t>((size_t)plan.bwin * n_out * PWORDS);
+            uint32_t *Y1o = ws.red[flip + 1].as<uint32_t>((size_t)plan.bwin * n_out * PWORDS);
+            uint32_t *Y2o = (Y1 || Y2) ? ws.red[flip + 2].as<uint32_t>((size_t)plan.bwin * n_out * PWORDS) : nullptr;
+            k_tile_reduce<F>(s, plan.bwin, X, Y1, Y2, n_in, n_out, T, shift, Xo, Y1o, Y2o);
+            X = Xo; Y1 = Y1o; Y2 = Y2o;
         }
-        n_in = n_out; shift += log_l; flip ^= 2;
+        n_in = n_out; shift += log_l; flip ^= 3;
     }
     dv.timer.mark(5, s);
     // 6. window fold + to affine
-    k_window_combine<F>(s, X, Y, plan.bwin, plan.c, d_out_xyzz, d_out_aff);
+    k_window_combine<F>(s, X, Y1, Y2, plan.bwin, plan.c, d_out_xyzz, d_out_aff);
     dv.timer.mark(6, s);
 }
 

@@ -52,13 +52,14 @@ void k_chunk_merge(stream_t s, size_t max_split, const uint32_t *split_list, con
 template <class F>
 void k_reduce_level(stream_t s, size_t threads, const uint32_t *X, const uint32_t *Y, uint32_t n_in, uint32_t n_out,
                     uint32_t L, uint32_t shift, uint32_t *Xo, uint32_t *Yo);
-// block-cooperative level: tile = T elements (power of two <= 256), grid (n_out, windows)
+// block-cooperative level: tile = T entries (power of two <= k_tile_entries()), grid (n_out, windows, X | Y blocks)
+uint32_t k_tile_entries();
 template <class F>
-void k_tile_reduce(stream_t s, uint32_t windows, const uint32_t *X, const uint32_t *Y, uint32_t n_in, uint32_t n_out,
-                   uint32_t T, uint32_t shift, uint32_t *Xo, uint32_t *Yo);
+void k_tile_reduce(stream_t s, uint32_t windows, const uint32_t *X, const uint32_t *Y1, const uint32_t *Y2, uint32_t n_in,
+                   uint32_t n_out, uint32_t T, uint32_t shift, uint32_t *Xo, uint32_t *Y1o, uint32_t *Y2o);
 template <class F>
-void k_window_combine(stream_t s, const uint32_t *X, const uint32_t *Y, uint32_t nwin, uint32_t c, uint32_t *out_xyzz,
-                      uint32_t *out_aff);
+void k_window_combine(stream_t s, const uint32_t *X, const uint32_t *Y, const uint32_t *Y2, uint32_t nwin, uint32_t c,
+                      uint32_t *out_xyzz, uint32_t *out_aff);
 template <class F>
 void k_partial_combine(stream_t s, const uint32_t *partials, uint32_t k, uint32_t *out_xyzz, uint32_t *out_aff);
 // table[w * n + i] = affine(2^(c w) * pts[i]) for w < nwin (w = 0 is a copy)

@@ -29,28 +29,23 @@ void k_reduce_level(stream_t s, size_t threads, const uint32_t *X, const uint32_
     launch<ReduceLevel<F>>(threads, s, X, Y, n_in, n_out, L, shift, Xo, Yo);
 }
 template <class F>
-void k_tile_reduce(stream_t s, uint32_t windows, const uint32_t *X, const uint32_t *Y, uint32_t n_in, uint32_t n_out,
-                   uint32_t T, uint32_t shift, uint32_t *Xo, uint32_t *Yo) {
+void k_tile_reduce(stream_t s, uint32_t windows, const uint32_t *X, const uint32_t *Y1, const uint32_t *Y2, uint32_t n_in,
+                   uint32_t n_out, uint32_t T, uint32_t shift, uint32_t *Xo, uint32_t *Y1o, uint32_t *Y2o) {
 #ifndef G16_EMU
-    // T = entries per tile = threads * TILE_K
-    uint32_t threads = T / TILE_K < 32 ? 32 : T / TILE_K;
-    size_t smem = (size_t)threads * 4 * F::N * sizeof(uint32_t);
-    static bool configured = false;
-    if (!configured) {
-        G16_CUDA_CHECK(cudaFuncSetAttribute(tile_reduce_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        configured = true;
-    }
-    tile_reduce_kernel<F><<<dim3(n_out, windows), threads, smem, s>>>(X, Y, n_in, n_out, T, shift, Xo, Yo);
+    // T = entries per tile; elements (quads of lanes) = T / TILE_K, at least one warp of 8
+    uint32_t elems = T / TILE_K < 8 ? 8 : T / TILE_K;
+    size_t smem = (size_t)elems * (4 * F::N + 1) * sizeof(uint32_t);
+    tile_reduce_kernel<F><<<dim3(n_out, windows, (Y1 || Y2) ? 2 : 1), 4 * elems, smem, s>>>(X, Y1, Y2, n_in, n_out, T, shift, Xo, Y1o, Y2o);
     G16_CUDA_CHECK(cudaGetLastError());
     note_launch();
 #else
-    launch<TileReduceSerial<F>>((size_t)windows * n_out, s, X, Y, n_in, n_out, T, shift, Xo, Yo);
+    launch<TileReduceSerial<F>>((size_t)windows * n_out, s, X, Y1, Y2, n_in, n_out, T, shift, Xo, Y1o, Y2o);
 #endif
 }
 template <class F>
-void k_window_combine(stream_t s, const uint32_t *X, const uint32_t *Y, uint32_t nwin, uint32_t c, uint32_t *out_xyzz,
-                      uint32_t *out_aff) {
-    launch<WindowCombine<F>>(1, s, X, Y, nwin, c, out_xyzz, out_aff);
+void k_window_combine(stream_t s, const uint32_t *X, const uint32_t *Y, const uint32_t *Y2, uint32_t nwin, uint32_t c,
+                      uint32_t *out_xyzz, uint32_t *out_aff) {
+    launch<WindowCombine<F>>(1, s, X, Y, Y2, nwin, c, out_xyzz, out_aff);
 }
 template <class F>
 void k_partial_combine(stream_t s, const uint32_t *partials, uint32_t k, uint32_t *out_xyzz, uint32_t *out_aff) {

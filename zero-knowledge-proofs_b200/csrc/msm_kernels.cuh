@@ -9,6 +9,7 @@
 // The result is the same group element, returned as the canonical affine point.
 #pragma once
 #include "ec.cuh"
+#include "quad.cuh"
 #include "kernel_api.cuh"
 
 namespace g16 {
@@ -341,88 +342,113 @@ struct ReduceLevel {
     }
 };
 
-// Block-cooperative level of the same reduction for the upper, latency-bound part of the tree: one
-// thread per element, TILE elements per block.  A suffix scan gives P_j = sum_{k >= j} X_k, so that
-//   X' = P_0   and   sum_j j X_j = sum_{j >= 1} P_j   (one tree reduction),
-// i.e. 2 log2(TILE) dependent additions per level instead of 3 TILE for a serial walk.
-// Shared memory holds one XYZZ per thread, stored word-major (conflict free).
+// Block-cooperative level of the same reduction for the upper, latency-bound part of the tree.  From here
+// on a level carries THREE arrays: X (to be weighted by index), Y1 (weighted partials produced by the X
+// blocks of the previous level) and Y2 (plain sums of the previous level's Y1 + Y2); the total is
+// sum Y1 + sum Y2 + 2^shift * sum_i i X_i.  Splitting Y keeps the two halves of a level independent:
+//   X blocks (blockIdx.z == 0): every element (a quad of lanes, see quad.cuh) folds TILE_K consecutive
+//       entries, a suffix scan over the block's elements gives P_j = sum_{k >= j} S_k, so that
+//       X' = P_0 and sum_j j X_j = sum_j lw_j + TILE_K sum_{j >= 1} P_j (one tree), then `shift` doublings;
+//   Y blocks (blockIdx.z == 1): plain sum of the tile's Y1 and Y2 entries (fold + tree).
+// Every addition is the 4-lane cooperative one: a level costs ~2 log2(T) + 2 TILE_K dependent additions of
+// 4 multiplication latencies each.  Shared memory holds one XYZZ per element, element-major with an odd
+// stride (conflict free for the quad-broadcast reads).
+constexpr int TILE_K = 4;        // consecutive entries folded serially by each element before the block scan
+constexpr int TILE_ELEMS = 64;   // elements (quads) per block -> 256 threads, TILE_K * TILE_ELEMS entries per tile
 #if !defined(G16_EMU) && defined(__CUDACC__)
 template <class F>
-__device__ __forceinline__ void tile_put(uint32_t *sm, int T, int j, const XYZZ<F> &p) {
+__device__ __forceinline__ void tile_put(uint32_t *sm, int e, int q, const XYZZ<F> &p) {
+    constexpr int W = 4 * F::N, QW = W / 4;
     const uint32_t *s = reinterpret_cast<const uint32_t *>(&p);
+    uint32_t *d = sm + (size_t)e * (W + 1);
 #pragma unroll
-    for (int k = 0; k < 4 * F::N; ++k) sm[k * T + j] = s[k];
+    for (int k = 0; k < W; ++k)
+        if (k / QW == q) d[k] = s[k];   // every lane of the quad writes its quarter
 }
 template <class F>
-__device__ __forceinline__ XYZZ<F> tile_get(const uint32_t *sm, int T, int j) {
+__device__ __forceinline__ XYZZ<F> tile_get(const uint32_t *sm, int e) {
+    constexpr int W = 4 * F::N;
     XYZZ<F> p;
     uint32_t *d = reinterpret_cast<uint32_t *>(&p);
+    const uint32_t *s = sm + (size_t)e * (W + 1);
 #pragma unroll
-    for (int k = 0; k < 4 * F::N; ++k) d[k] = sm[k * T + j];
+    for (int k = 0; k < W; ++k) d[k] = s[k];
     return p;
 }
-constexpr int TILE_K = 4;   // consecutive entries folded serially by each thread before the block scan
 template <class F>
-__global__ void __launch_bounds__(256) tile_reduce_kernel(const uint32_t *X, const uint32_t *Y, uint32_t n_in, uint32_t n_out,
-                                                          uint32_t tile_entries, uint32_t shift, uint32_t *Xo, uint32_t *Yo) {
+__global__ void __launch_bounds__(4 * TILE_ELEMS, 2) tile_reduce_kernel(const uint32_t *X, const uint32_t *Y1, const uint32_t *Y2,
+                                                                     uint32_t n_in, uint32_t n_out, uint32_t tile_entries,
+                                                                     uint32_t shift, uint32_t *Xo, uint32_t *Y1o, uint32_t *Y2o) {
     extern __shared__ uint32_t sm[];
-    const int T = blockDim.x, j = threadIdx.x;     // T * TILE_K >= tile_entries
+    const int T = blockDim.x >> 2;                 // elements in this block; T * TILE_K >= tile_entries
+    const int e = threadIdx.x >> 2, q = threadIdx.x & 3;
+    const int warp_e0 = (threadIdx.x & ~31) >> 2;  // first element of this warp (8 elements per warp)
     const uint32_t w = blockIdx.y, g = blockIdx.x;
     const size_t base = (size_t)w * n_in;
-    const uint32_t local = (uint32_t)j * TILE_K;   // offset of this thread's entries inside the tile
+    const uint32_t local = (uint32_t)e * TILE_K;   // offset of this element's entries inside the tile
     const uint32_t first = g * tile_entries + local;
-    // per-thread fold of TILE_K entries: p = their sum, lw = sum_k k * x_k (local weights), y = sum of Y
-    XYZZ<F> p = XYZZ<F>::inf(), lw = XYZZ<F>::inf(), y = XYZZ<F>::inf();
-    for (int k = TILE_K - 1; k >= 0; --k) {
-        uint32_t i = first + k;
-        if (local + k < tile_entries && i < n_in) {
-            XYZZ<F> x = load_xyzz<F>(X, base + i);
-            xyzz_add_call(p, x);
-            if (Y) { XYZZ<F> yy = load_xyzz<F>(Y, base + i); xyzz_add_call(y, yy); }
-        }
-        if (k >= 1) xyzz_add_call(lw, p);      // after the loop: lw = sum_{k>=1} (suffix sum from k) = sum_k k x_k
-    }
-    // suffix scan of the thread sums (Hillis-Steele): p = P_j = sum_{t >= j} S_t
-    for (int d = 1; d < T; d <<= 1) {
-        tile_put<F>(sm, T, j, p);
-        __syncthreads();
-        if (j + d < T) {
-            XYZZ<F> q = tile_get<F>(sm, T, j + d);
-            xyzz_add_call(p, q);
-        }
-        __syncthreads();
-    }
-    if (j == 0) store_xyzz<F>(Xo, (size_t)w * n_out + g, p);
-    // sum_i i x_i over the tile = sum_j lw_j + TILE_K * sum_{j >= 1} P_j
-    XYZZ<F> v = j >= 1 ? p : XYZZ<F>::inf();
+    if (blockIdx.z == 1) {
+        // ---- plain sum of the already weighted partials
+        XYZZ<F> y = XYZZ<F>::inf();
 #pragma unroll 1
-    for (int k = 1; k < TILE_K; k <<= 1) xyzz_dbl_call(v);
-    xyzz_add_call(v, lw);
-    for (int d = T >> 1; d >= 1; d >>= 1) {
-        tile_put<F>(sm, T, j, v);
-        __syncthreads();
-        if (j < d) {
-            XYZZ<F> q = tile_get<F>(sm, T, j + d);
-            xyzz_add_call(v, q);
+        for (int k = 0; k < TILE_K; ++k) {
+            uint32_t i = first + k;
+            bool live = local + k < tile_entries && i < n_in;
+            if (Y1) { XYZZ<F> t = live ? load_xyzz<F>(Y1, base + i) : XYZZ<F>::inf(); xyzz_add_quad(y, t, q); }
+            if (Y2) { XYZZ<F> t = live ? load_xyzz<F>(Y2, base + i) : XYZZ<F>::inf(); xyzz_add_quad(y, t, q); }
         }
-        __syncthreads();
-    }
-    // sum of the already weighted partials
-    if (Y) {
+#pragma unroll 1
         for (int d = T >> 1; d >= 1; d >>= 1) {
-            tile_put<F>(sm, T, j, y);
+            tile_put<F>(sm, e, q, y);
             __syncthreads();
-            if (j < d) {
-                XYZZ<F> q = tile_get<F>(sm, T, j + d);
-                xyzz_add_call(y, q);
+            if (warp_e0 < d) {
+                XYZZ<F> t = e < d ? tile_get<F>(sm, e + d) : XYZZ<F>::inf();
+                xyzz_add_quad(y, t, q);
             }
             __syncthreads();
         }
+        if (threadIdx.x == 0) store_xyzz<F>(Y2o, (size_t)w * n_out + g, y);
+        return;
     }
-    if (j == 0) {
-        for (uint32_t s = 0; s < shift; ++s) xyzz_dbl_call(v);
-        xyzz_add_call(v, y);
-        store_xyzz<F>(Yo, (size_t)w * n_out + g, v);
+    // ---- X block.  Per-element fold of TILE_K entries: p = their sum, lw = sum_k k * x_k (local weights)
+    XYZZ<F> p = XYZZ<F>::inf(), lw = XYZZ<F>::inf();
+#pragma unroll 1
+    for (int k = TILE_K - 1; k >= 0; --k) {
+        uint32_t i = first + k;
+        bool live = local + k < tile_entries && i < n_in;
+        XYZZ<F> x = live ? load_xyzz<F>(X, base + i) : XYZZ<F>::inf();
+        xyzz_add_quad(p, x, q);
+        if (k >= 1) xyzz_add_quad(lw, p, q);   // after the loop: lw = sum_{k>=1} (suffix sum from k) = sum_k k x_k
+    }
+    // suffix scan of the element sums (Hillis-Steele): p = P_e = sum_{t >= e} S_t
+#pragma unroll 1
+    for (int d = 1; d < T; d <<= 1) {
+        tile_put<F>(sm, e, q, p);
+        __syncthreads();
+        XYZZ<F> t = e + d < T ? tile_get<F>(sm, e + d) : XYZZ<F>::inf();
+        xyzz_add_quad(p, t, q);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) store_xyzz<F>(Xo, (size_t)w * n_out + g, p);
+    // sum_i i x_i over the tile = sum_e lw_e + TILE_K * sum_{e >= 1} P_e
+    XYZZ<F> v = e >= 1 ? p : XYZZ<F>::inf();
+#pragma unroll 1
+    for (int k = 1; k < TILE_K; k <<= 1) xyzz_dbl_quad(v, q);
+    xyzz_add_quad(v, lw, q);
+#pragma unroll 1
+    for (int d = T >> 1; d >= 1; d >>= 1) {
+        tile_put<F>(sm, e, q, v);
+        __syncthreads();
+        if (warp_e0 < d) {
+            XYZZ<F> t = e < d ? tile_get<F>(sm, e + d) : XYZZ<F>::inf();
+            xyzz_add_quad(v, t, q);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x < 32) {
+#pragma unroll 1
+        for (uint32_t s = 0; s < shift; ++s) xyzz_dbl_quad(v, q);
+        if (threadIdx.x == 0) store_xyzz<F>(Y1o, (size_t)w * n_out + g, v);
     }
 }
 #endif
@@ -430,8 +456,8 @@ __global__ void __launch_bounds__(256) tile_reduce_kernel(const uint32_t *X, con
 template <class F>
 struct TileReduceSerial {
     static constexpr int BLOCK = 32;
-    G16_HD static void run(size_t t, const uint32_t *X, const uint32_t *Y, uint32_t n_in, uint32_t n_out, uint32_t T,
-                           uint32_t shift, uint32_t *Xo, uint32_t *Yo) {
+    G16_HD static void run(size_t t, const uint32_t *X, const uint32_t *Y1, const uint32_t *Y2, uint32_t n_in, uint32_t n_out,
+                           uint32_t T, uint32_t shift, uint32_t *Xo, uint32_t *Y1o, uint32_t *Y2o) {
         uint32_t w = (uint32_t)(t / n_out), g = (uint32_t)(t % n_out);
         size_t base = (size_t)w * n_in;
         uint32_t lo = g * T, hi = lo + T < n_in ? lo + T : n_in;
@@ -444,10 +470,11 @@ struct TileReduceSerial {
         XYZZ<F> x0 = load_xyzz<F>(X, base + lo);
         xyzz_add_call(running, x0);
         for (uint32_t s = 0; s < shift; ++s) xyzz_dbl_call(acc);
-        if (Y) for (uint32_t i = lo; i < hi; ++i) { XYZZ<F> y = load_xyzz<F>(Y, base + i); xyzz_add_call(ysum, y); }
-        xyzz_add_call(acc, ysum);
+        if (Y1) for (uint32_t i = lo; i < hi; ++i) { XYZZ<F> y = load_xyzz<F>(Y1, base + i); xyzz_add_call(ysum, y); }
+        if (Y2) for (uint32_t i = lo; i < hi; ++i) { XYZZ<F> y = load_xyzz<F>(Y2, base + i); xyzz_add_call(ysum, y); }
         store_xyzz<F>(Xo, (size_t)w * n_out + g, running);
-        store_xyzz<F>(Yo, (size_t)w * n_out + g, acc);
+        store_xyzz<F>(Y1o, (size_t)w * n_out + g, acc);
+        if (Y1 || Y2) store_xyzz<F>(Y2o, (size_t)w * n_out + g, ysum);
     }
 };
 
@@ -457,7 +484,7 @@ struct TileReduceSerial {
 template <class F>
 struct WindowCombine {
     static constexpr int BLOCK = 32;
-    G16_HD static void run(size_t, const uint32_t *X, const uint32_t *Y, uint32_t nwin, uint32_t c,
+    G16_HD static void run(size_t, const uint32_t *X, const uint32_t *Y, const uint32_t *Y2, uint32_t nwin, uint32_t c,
                            uint32_t *out_xyzz, uint32_t *out_aff) {
         XYZZ<F> acc = XYZZ<F>::inf();
         for (uint32_t w = nwin; w-- > 0;) {
@@ -466,6 +493,10 @@ struct WindowCombine {
             xyzz_add_call(acc, x);
             if (Y) {
                 XYZZ<F> y = load_xyzz<F>(Y, w);
+                xyzz_add_call(acc, y);
+            }
+            if (Y2) {
+                XYZZ<F> y = load_xyzz<F>(Y2, w);
                 xyzz_add_call(acc, y);
             }
         }
