@@ -157,6 +157,64 @@ int g16_prove(g16_ctx *ctx, const g16_pk *pk, const uint64_t *assignment_fr, siz
 int g16_quotient_h(g16_ctx *ctx, const uint64_t *a_evals, const uint64_t *b_evals, const uint64_t *c_evals, size_t n,
                    uint64_t *h_coeffs);
 
+/* ---- sparse R1CS: setup and prove for real circuits (rows 1-3 chained on the device) -------- */
+/* The reference turns an R1CS into dense per-variable polynomials (`QAP::from_r1cs`,
+ * crates/groth16-qap/src/lib.rs:95-187), Theta(constraints x variables) in memory.  These entry points keep the
+ * three constraint matrices sparse and give the same values in O(non-zeros):
+ *   g16_r1cs_domain_evals   <A-row i, w>, <B-row i, w>, <C-row i, w> for the n = next_power_of_two(constraints)
+ *                           domain points = the evaluations of sum_k w_k A_k(x) etc. that
+ *                           `compute_quotient_polynomial` (qap/src/lib.rs:225-271) sums densely
+ *   g16_r1cs_eval_at        A_j(s), B_j(s), C_j(s) for every variable j = `qap.a_polys[j].evaluate(&s)`
+ *                           (crates/groth16-setup/src/lib.rs:174-182), through the Lagrange basis at s
+ *   g16_setup_crs           `CRS::generate_from_qap` (crates/groth16-setup/src/lib.rs:141-268): parameter checks,
+ *                           64-bit truncations, IC / H exponents, and every `(gen * fr).into_affine()`
+ *   g16_prove_r1cs          `Prover::prove` (crates/groth16-core/src/lib.rs:139-272) from the un-truncated witness:
+ *                           Witness::validate, quotient polynomial, truncations, the five MSMs
+ * A matrix is CSR over the constraints: row_ptr[num_constraints + 1], col[nnz] (variable indices; entries with
+ * col >= num_variables are ignored like qap/src/lib.rs:121-138 does), val[nnz x 4 u64] (Fr, Montgomery).  A
+ * (row, variable) pair may appear at most once per matrix.  Single-device contexts only. */
+typedef struct g16_r1cs g16_r1cs;
+typedef struct g16_csr {
+    const uint32_t *row_ptr;
+    const uint32_t *col;
+    const uint64_t *val;
+} g16_csr;
+int g16_r1cs_upload(g16_ctx *ctx, size_t num_constraints, size_t num_variables, const g16_csr *a, const g16_csr *b,
+                    const g16_csr *c, g16_r1cs **out);
+void g16_r1cs_free(g16_r1cs *r1cs);
+size_t g16_r1cs_domain_size(const g16_r1cs *r1cs);
+/* assignment: num_vars x 4 u64 (must equal num_variables, else G16_ERR_LENGTH); *_evals: domain_size x 4 u64 */
+int g16_r1cs_domain_evals(g16_ctx *ctx, const g16_r1cs *r1cs, const uint64_t *assignment, size_t num_vars,
+                          uint64_t *a_evals, uint64_t *b_evals, uint64_t *c_evals);
+/* s is used as given (no truncation); *_vals: num_variables x 4 u64 */
+int g16_r1cs_eval_at(g16_ctx *ctx, const g16_r1cs *r1cs, const uint64_t s[4], uint64_t *a_vals, uint64_t *b_vals,
+                     uint64_t *c_vals);
+/* Outputs of g16_setup_crs on the host, ark layout; every pointer may be NULL (not wanted).  Lengths:
+ * a_g1, b_g1, b_g2: num_variables; ic_g1: num_variables - num_public - 1 (ProvingKey.ic_g1); vk_ic_g1:
+ * num_public + 1 (VerificationKey.ic_g1); h_g1: domain size (= qap.degree()). */
+typedef struct g16_crs_host {
+    uint64_t *alpha_g1, *beta_g1, *delta_g1;   /* 12 u64 each */
+    uint64_t *beta_g2, *gamma_g2, *delta_g2;   /* 24 u64 each */
+    uint64_t *a_g1; uint8_t *a_g1_inf;
+    uint64_t *b_g1; uint8_t *b_g1_inf;
+    uint64_t *b_g2; uint8_t *b_g2_inf;
+    uint64_t *ic_g1; uint8_t *ic_g1_inf;
+    uint64_t *vk_ic_g1; uint8_t *vk_ic_g1_inf;
+    uint64_t *h_g1; uint8_t *h_g1_inf;
+} g16_crs_host;
+/* alpha .. s: the five SetupParams (4 u64 Montgomery each, full width; the reference truncates them itself where
+ * it does).  out may be NULL; pk_out (may be NULL) receives the device-resident proving key, ready for g16_prove /
+ * g16_prove_r1cs without a host round trip.  Errors mirror SetupError::InvalidParams. */
+int g16_setup_crs(g16_ctx *ctx, const g16_r1cs *r1cs, const uint64_t alpha[4], const uint64_t beta[4],
+                  const uint64_t gamma[4], const uint64_t delta[4], const uint64_t s[4], size_t num_public,
+                  g16_crs_host *out, g16_pk **pk_out);
+/* assignment: the witness as the reference holds it (F elements, NOT truncated).  Errors: G16_ERR_LENGTH
+ * (assignment length), G16_ERR_INVALID "Invalid witness: ..." (Witness::validate) or "Polynomial division
+ * failed" (QAPError::PolynomialDivisionFailed). */
+int g16_prove_r1cs(g16_ctx *ctx, const g16_pk *pk, const g16_r1cs *r1cs, const uint64_t *assignment, size_t num_vars,
+                   const uint64_t r[4], const uint64_t s[4], uint64_t a_xy[12], uint8_t *a_inf, uint64_t b_xy[24],
+                   uint8_t *b_inf, uint64_t c_xy[12], uint8_t *c_inf);
+
 /* ---- test hooks (used by tests/ and bench.py only) ------------------------------------------ */
 /* kernels launched by the library since it was loaded */
 unsigned long long g16_launch_count(void);

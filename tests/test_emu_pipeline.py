@@ -46,3 +46,15 @@ def test_emu_quotient_polynomial(emu_ctx):
     import quotient_cases as qc
     qc.check_toy_circuits(emu_ctx)
     qc.check_random_polynomials(emu_ctx, log_sizes=(0, 1, 2, 3, 5))
+
+
+def test_emu_r1cs_evaluations(emu_ctx):
+    import r1cs_cases as rc
+    rc.check_evals_small(emu_ctx)
+    rc.check_evals_long_lines(emu_ctx, m=300)
+
+
+def test_emu_r1cs_setup_and_prove(emu_ctx):
+    import r1cs_cases as rc
+    rc.check_setup_and_prove(emu_ctx, circuits=rc.CIRCUITS[:3])
+    rc.check_errors(emu_ctx)

@@ -28,3 +28,21 @@ def test_quotient_polynomial_ntt(gpu_ctx):
     import quotient_cases as qc
     qc.check_toy_circuits(gpu_ctx)
     qc.check_random_polynomials(gpu_ctx, log_sizes=(0, 1, 2, 3, 5, 8, 10))
+
+
+def test_r1cs_evaluations(gpu_ctx):
+    import r1cs_cases as rc
+    rc.check_evals_small(gpu_ctx)
+    rc.check_evals_long_lines(gpu_ctx, m=700)
+
+
+def test_r1cs_setup_and_prove(gpu_ctx):
+    import r1cs_cases as rc
+    golden = os.path.join(os.path.dirname(GOLDEN), "r1cs_proofs.json")
+    rc.check_setup_and_prove(gpu_ctx, golden=json.load(open(golden)))
+    rc.check_errors(gpu_ctx)
+
+
+def test_r1cs_large_polynomial_identity(gpu_ctx, oracle):
+    import r1cs_cases as rc
+    rc.check_large_properties(gpu_ctx, oracle, log_m=12)

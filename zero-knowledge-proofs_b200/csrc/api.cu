@@ -1,55 +1,7 @@
 // C ABI of libg16cuda.so (declared in include/g16_cuda.h).  Also compiled as plain C++ with
 // -DG16_EMU by tests/emu (see rt.cuh) -- that build is test infrastructure only.
 #include "../../include/g16_cuda.h"
-#include "engine.cuh"
-
-using namespace g16;
-
-struct g16_ctx { Context c; };
-struct g16_bases { std::unique_ptr<Bases> b; };
-
-struct g16_pk {
-    Context *ctx = nullptr;
-    // resident arrays with the ad-hoc single points prepended (see g16_prove)
-    std::unique_ptr<Bases> a;    // [alpha_g1, delta_g1, a_g1...]
-    std::unique_ptr<Bases> b2;   // [beta_g2, delta_g2, b_g2...]
-    std::unique_ptr<Bases> b1;   // [beta_g1, b_g1...]
-    std::unique_ptr<Bases> ic;   // ic_g1
-    std::unique_ptr<Bases> h;    // h_g1
-    size_t a_len = 0, b1_len = 0, b2_len = 0, ic_len = 0, h_len = 0, num_public = 0;
-};
-
-static thread_local std::string g_create_error;
-static const uint64_t FR_ONE_MONT[4] = {0x00000001fffffffeULL, 0x5884b7fa00034802ULL, 0x998c4fefecbc4ff5ULL,
-                                        0x1824b159acc5056fULL};
-
-
-template <class Fn>
-static int guarded(g16_ctx *ctx, Fn &&fn) {
-    try {
-        fn();
-        return G16_OK;
-    } catch (const Error &e) {
-        if (ctx) ctx->c.err = e.msg; else g_create_error = e.msg;
-        return e.code;
-    } catch (const std::bad_alloc &) {
-        if (ctx) ctx->c.err = "host allocation failed"; else g_create_error = "host allocation failed";
-        return G16_ERR_OOM;
-    } catch (...) {
-        if (ctx) ctx->c.err = "unknown error"; else g_create_error = "unknown error";
-        return G16_ERR_INVALID;
-    }
-}
-
-static void require(bool ok, const char *what) {
-    if (!ok) throw Error{G16_ERR_INVALID, what};
-}
-
-static Device &single_device(g16_ctx *ctx) {
-    require(ctx->c.devs.size() == 1, "this entry point needs a single-device context");
-    set_device(ctx->c.devs[0].id);
-    return ctx->c.devs[0];
-}
+#include "api_common.cuh"
 
 extern "C" {
 
@@ -129,7 +81,7 @@ void g16_ctx_destroy(g16_ctx *ctx) {
     delete ctx;
 }
 
-const char *g16_last_error(const g16_ctx *ctx) { return ctx ? ctx->c.err.c_str() : g_create_error.c_str(); }
+const char *g16_last_error(const g16_ctx *ctx) { return ctx ? ctx->c.err.c_str() : create_error().c_str(); }
 
 int g16_ctx_set_stream(g16_ctx *ctx, void *cuda_stream) {
     if (!ctx) return G16_ERR_INVALID;
@@ -427,13 +379,14 @@ int g16_pk_precompute(g16_ctx *ctx, g16_pk *pk) {
 void g16_pk_free(g16_pk *pk) { delete pk; }
 
 
+extern "C++" {
 // Single-device fast path of the prove schedule: the assignment is copied to the device once, every MSM
 // gets its (prefix ++ assignment) scalar vector by a device-to-device copy, the five big MSMs run on
 // five lanes, and the ad-hoc terms of pi_C (H, s*pi_A, r*pi_B') are taken from the other lanes' results
 // on the device -- the host waits exactly once, at the end.
-static void prove_single_device(Context *c, const g16_pk *pk, const uint64_t *w, size_t num_vars, const uint64_t *h,
-                                size_t num_h, const uint64_t *r, const uint64_t *s, uint64_t *a_xy, uint8_t *a_inf,
-                                uint64_t *b_xy, uint8_t *b_inf, uint64_t *c_xy, uint8_t *c_inf) {
+void prove_single_device(Context *c, const g16_pk *pk, const uint64_t *w, size_t num_vars, const uint64_t *h,
+                         size_t num_h, const uint64_t *r, const uint64_t *s, uint64_t *a_xy, uint8_t *a_inf,
+                         uint64_t *b_xy, uint8_t *b_inf, uint64_t *c_xy, uint8_t *c_inf, const ProveDeviceInputs *dev) {
     constexpr size_t PW1 = 48, AW1 = 25, PW2 = 96, AW2 = 49;
     Device &d0 = c->devs[0];
     set_device(d0.id);
@@ -448,8 +401,13 @@ static void prove_single_device(Context *c, const g16_pk *pk, const uint64_t *w,
     put(5, FR_ONE_MONT); put(6, s); put(7, r);   // ad-hoc terms of pi_C: [1 * H, s * pi_A, r * pi_B']
 
     // assignment: one H2D, shared by four MSMs
-    uint32_t *d_w = LA.ws.prove_w.as<uint32_t>(num_vars * 8 + 8);
-    copy_h2d(d_w, w, num_vars * 32, LA.stream);
+    // (or already on the device, produced on lane 0's stream by the R1CS path)
+    const uint32_t *d_w = dev ? dev->d_w : nullptr;
+    if (!d_w) {
+        uint32_t *buf = LA.ws.prove_w.as<uint32_t>(num_vars * 8 + 8);
+        copy_h2d(buf, w, num_vars * 32, LA.stream);
+        d_w = buf;
+    }
     uint32_t *d_misc = LA.ws.prove_misc.as<uint32_t>(16 * 8 + 3 * 24 + 2 * PW1 + AW1 + 64);
     uint32_t *d_small = d_misc;                       // 16 scalars
     uint32_t *d_adhoc_pts = d_misc + 16 * 8;          // 3 packed G1 points
@@ -457,6 +415,7 @@ static void prove_single_device(Context *c, const g16_pk *pk, const uint64_t *w,
     uint32_t *d_c_aff = d_cparts + 2 * PW1;           // pi_C affine
     copy_h2d(d_small, hs.data(), 16 * 32, LA.stream);
     for (Device *l : {&LB, &LB1, &LC}) stream_wait(l->stream, LA.stream);
+    if (dev) stream_wait(LH.stream, LA.stream);
 
     auto prefixed = [&](Device &L, size_t slot, size_t k, size_t n) {
         uint32_t *d = L.ws.scalars.as<uint32_t>((k + n) * 8 + 8);
@@ -470,9 +429,11 @@ static void prove_single_device(Context *c, const g16_pk *pk, const uint64_t *w,
     msm_run<Fq>(LA, pk->a->shards[0], prefixed(LA, 0, 2, na), na + 2, true, co, nullptr, oa);
     uint32_t *ob = LB.ws.out.as<uint32_t>(PW2 + AW2) + PW2;
     msm_run<Fq2>(LB, pk->b2->shards[0], prefixed(LB, 2, 2, nb2), nb2 + 2, true, co, nullptr, ob);
-    size_t nh = h ? std::min(num_h, pk->h_len) : 0;
+    size_t nh = (h || (dev && dev->d_h)) ? std::min(num_h, pk->h_len) : 0;
     uint32_t *oh = LH.ws.out.as<uint32_t>(PW1 + AW1) + PW1;
-    {
+    if (dev && dev->d_h) {
+        msm_run<Fq>(LH, pk->h->shards[0], dev->d_h, nh, true, co, nullptr, oh);
+    } else {
         uint32_t *d_h = LH.ws.scalars.as<uint32_t>(nh * 8 + 8);
         copy_h2d(d_h, h, nh * 32, LH.stream);
         msm_run<Fq>(LH, pk->h->shards[0], d_h, nh, true, co, nullptr, oh);     // nh == 0 -> identity
@@ -496,12 +457,14 @@ static void prove_single_device(Context *c, const g16_pk *pk, const uint64_t *w,
     copy_d2h(ra, oa, AW1 * 4, LA.stream);
     copy_d2h(rb, ob, AW2 * 4, LB.stream);
     copy_d2h(rc, d_c_aff, AW1 * 4, LC.stream);
+    if (dev && dev->d_flags && dev->flags_out) copy_d2h(dev->flags_out, dev->d_flags, 8, LA.stream);
     for (Device *l : {&LA, &LB, &LH, &LB1, &LC}) stream_sync(l->stream);
     memcpy(a_xy, ra, 96); memcpy(b_xy, rb, 192); memcpy(c_xy, rc, 96);
     if (a_inf) *a_inf = (uint8_t)ra[24];
     if (b_inf) *b_inf = (uint8_t)rb[48];
     if (c_inf) *c_inf = (uint8_t)rc[24];
 }
+}  // extern "C++"
 
 // The MSM schedule of Prover::prove (crates/groth16-core/src/lib.rs:164-271).  The reference
 // builds fresh (scalar, point) lists with zero scalars filtered out; here the CRS arrays stay
@@ -518,7 +481,7 @@ int g16_prove(g16_ctx *ctx, const g16_pk *pk, const uint64_t *assignment_fr, siz
         require(num_vars > pk->num_public, "assignment shorter than the public inputs");
         Context *c = &ctx->c;
         if (c->devs.size() == 1) {
-            prove_single_device(c, pk, assignment_fr, num_vars, h_coeffs, num_h, r, s, a_xy, a_inf, b_xy, b_inf, c_xy, c_inf);
+            prove_single_device(c, pk, assignment_fr, num_vars, h_coeffs, num_h, r, s, a_xy, a_inf, b_xy, b_inf, c_xy, c_inf, nullptr);
             return;
         }
         auto put = [](std::vector<uint64_t> &v, const uint64_t *x) { v.insert(v.end(), x, x + 4); };

@@ -482,25 +482,26 @@ void msm_host(Context *ctx, const Bases *bases, const uint64_t *scalars, size_t 
 //   evals: host, 3 arrays (a, b, c) of n Fr each (Montgomery), n = 2^log_n;  h: host, n Fr
 // Returns false when A*B - C does not vanish on the domain (the reference's PolynomialDivisionFailed).
 // ---------------------------------------------------------------------------------------
-inline bool quotient_host(Device &dv, const uint64_t *a, const uint64_t *b, const uint64_t *c, uint32_t log_n, uint64_t *h) {
+// constants + twiddles of the size-2^log_n domain, cached per workspace
+inline const uint32_t *ntt_prepare(Device &dv, uint32_t log_n) {
     Workspace &ws = dv.ws;
-    stream_t s = dv.stream;
     uint32_t n = 1u << log_n;
-    uint32_t *abc = ws.ntt_abc.as<uint32_t>((size_t)3 * n * 8 + 8);
-    uint32_t *flag = abc + (size_t)3 * n * 8;
     uint32_t *tw = ws.ntt_tw.as<uint32_t>((size_t)n * 8 + 8);       // tw[n/2] then twi[n/2]
-    uint32_t *twi = tw + (size_t)(n / 2) * 8;
     uint32_t *consts = ws.ntt_consts.as<uint32_t>(k_ntt_const_words());
-    uint32_t *out = ws.ntt_out.as<uint32_t>((size_t)n * 8);
-    copy_h2d(abc, a, (size_t)n * 32, s);
-    copy_h2d(abc + (size_t)n * 8, b, (size_t)n * 32, s);
-    copy_h2d(abc + (size_t)2 * n * 8, c, (size_t)n * 32, s);
-    dev_memset(flag, 0, 4, s);
     if (ws.ntt_log_n != log_n) {
-        k_ntt_setup(s, log_n, consts);
-        if (n >= 2) k_ntt_twiddles(s, n, consts, tw, twi);
+        k_ntt_setup(dv.stream, log_n, consts);
+        if (n >= 2) k_ntt_twiddles(dv.stream, n, consts, tw, tw + (size_t)(n / 2) * 8);
         ws.ntt_log_n = log_n;
     }
+    return consts;
+}
+// abc: device, the evaluations of A, B, C back to back (3 n Fr, overwritten); flag: device word that counts the
+// rows where A*B != C; out: device, n coefficients of H.  Asynchronous on dv.stream.
+inline void quotient_device(Device &dv, uint32_t log_n, uint32_t *abc, uint32_t *flag, uint32_t *out) {
+    stream_t s = dv.stream;
+    uint32_t n = 1u << log_n;
+    const uint32_t *consts = ntt_prepare(dv, log_n);
+    const uint32_t *tw = (const uint32_t *)dv.ws.ntt_tw.p, *twi = tw + (size_t)(n / 2) * 8;
     k_ntt_check_vanish(s, abc, n, flag);
     // coefficients (bit-reversed), coset shift, values on the coset
     for (uint32_t half = n / 2; half >= 1; half >>= 1) k_ntt_stage(s, false, 3, abc, twi, n, half);
@@ -509,6 +510,19 @@ inline bool quotient_host(Device &dv, const uint64_t *a, const uint64_t *b, cons
     k_ntt_quotient_pointwise(s, abc, consts, n);
     for (uint32_t half = n / 2; half >= 1; half >>= 1) k_ntt_stage(s, false, 1, abc, twi, n, half);
     k_ntt_final_scale(s, abc, consts, n, log_n, out);
+}
+inline bool quotient_host(Device &dv, const uint64_t *a, const uint64_t *b, const uint64_t *c, uint32_t log_n, uint64_t *h) {
+    Workspace &ws = dv.ws;
+    stream_t s = dv.stream;
+    uint32_t n = 1u << log_n;
+    uint32_t *abc = ws.ntt_abc.as<uint32_t>((size_t)3 * n * 8 + 8);
+    uint32_t *flag = abc + (size_t)3 * n * 8;
+    uint32_t *out = ws.ntt_out.as<uint32_t>((size_t)n * 8);
+    copy_h2d(abc, a, (size_t)n * 32, s);
+    copy_h2d(abc + (size_t)n * 8, b, (size_t)n * 32, s);
+    copy_h2d(abc + (size_t)2 * n * 8, c, (size_t)n * 32, s);
+    dev_memset(flag, 0, 4, s);
+    quotient_device(dv, log_n, abc, flag, out);
     uint32_t bad = 0;
     copy_d2h(h, out, (size_t)n * 32, s);
     copy_d2h(&bad, flag, 4, s);

@@ -90,6 +90,19 @@ void k_ntt_quotient_pointwise(stream_t s, uint32_t *abc, const uint32_t *consts,
 void k_ntt_final_scale(stream_t s, const uint32_t *x, const uint32_t *consts, uint32_t n, uint32_t log_n, uint32_t *out);
 void k_ntt_check_vanish(stream_t s, const uint32_t *abc, uint32_t n, uint32_t *flag);
 
+// sparse R1CS (Fr), see r1cs_kernels.cuh.  Stacked CSR: `lines` lines, out[(t / seg) * seg_out + t % seg]
+void k_spmv(stream_t s, size_t lines, const uint32_t *line_ptr, const uint32_t *idx, const uint32_t *val, const uint32_t *vec,
+            uint32_t seg, uint32_t seg_out, const uint32_t *long_lines, size_t n_long, uint32_t *out);
+uint32_t k_spmv_long_threshold();
+void k_truncate64(stream_t s, size_t n, const uint32_t *in, uint32_t *out);
+size_t k_setup_scalar_words();
+void k_setup_scalars(stream_t s, const uint32_t *params, const uint32_t *consts, uint32_t log_n, uint32_t truncate, uint32_t *blk);
+void k_lagrange_at(stream_t s, size_t n, const uint32_t *consts, const uint32_t *blk, uint32_t *out);
+void k_crs_exponents(stream_t s, size_t num_vars, const uint32_t *vals, const uint32_t *blk, uint32_t num_public, uint32_t *ab,
+                     uint32_t *ic);
+void k_crs_h_exponents(stream_t s, size_t n, const uint32_t *blk, uint32_t *h);
+void k_validate_row(stream_t s, const uint32_t *abc, uint32_t n, uint32_t *flag);
+
 // test hooks
 void k_debug_fq_op(stream_t s, size_t n, int op, const uint32_t *a, const uint32_t *b, uint32_t *out);
 void k_debug_fr_from_mont(stream_t s, size_t n, const uint32_t *a, uint32_t *out);

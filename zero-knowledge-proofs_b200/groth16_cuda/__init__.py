@@ -40,6 +40,8 @@ EXPORTS = [
     "g16_g1_fixed_base_mul", "g16_g2_fixed_base_mul",
     "g16_g1_fixed_base_mul_device", "g16_g2_fixed_base_mul_device",
     "g16_pk_upload", "g16_pk_free", "g16_prove", "g16_pk_precompute", "g16_quotient_h",
+    "g16_r1cs_upload", "g16_r1cs_free", "g16_r1cs_domain_size", "g16_r1cs_domain_evals", "g16_r1cs_eval_at",
+    "g16_setup_crs", "g16_prove_r1cs",
 ]
 
 
@@ -62,6 +64,17 @@ class _PkHost(ctypes.Structure):
         ("h_g1", ctypes.c_void_p), ("h_g1_inf", ctypes.c_void_p), ("h_len", ctypes.c_size_t),
         ("num_public", ctypes.c_size_t),
     ]
+
+
+class _Csr(ctypes.Structure):
+    _fields_ = [("row_ptr", ctypes.c_void_p), ("col", ctypes.c_void_p), ("val", ctypes.c_void_p)]
+
+
+class _CrsHost(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in (
+        "alpha_g1", "beta_g1", "delta_g1", "beta_g2", "gamma_g2", "delta_g2",
+        "a_g1", "a_g1_inf", "b_g1", "b_g1_inf", "b_g2", "b_g2_inf", "ic_g1", "ic_g1_inf",
+        "vk_ic_g1", "vk_ic_g1_inf", "h_g1", "h_g1_inf")]
 
 
 _libs = {}
@@ -106,6 +119,16 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.g16_pk_free.restype = None
     lib.g16_prove.argtypes = [vp, vp, vp, sz, vp, sz, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.g16_quotient_h.argtypes = [vp, vp, vp, vp, sz, vp]
+    lib.g16_r1cs_upload.argtypes = [vp, sz, sz, ctypes.POINTER(_Csr), ctypes.POINTER(_Csr), ctypes.POINTER(_Csr),
+                                    ctypes.POINTER(vp)]
+    lib.g16_r1cs_free.argtypes = [vp]
+    lib.g16_r1cs_free.restype = None
+    lib.g16_r1cs_domain_size.argtypes = [vp]
+    lib.g16_r1cs_domain_size.restype = sz
+    lib.g16_r1cs_domain_evals.argtypes = [vp, vp, vp, sz, vp, vp, vp]
+    lib.g16_r1cs_eval_at.argtypes = [vp, vp, vp, vp, vp, vp]
+    lib.g16_setup_crs.argtypes = [vp, vp, vp, vp, vp, vp, vp, sz, ctypes.POINTER(_CrsHost), ctypes.POINTER(vp)]
+    lib.g16_prove_r1cs.argtypes = [vp, vp, vp, vp, sz, vp, vp, vp, vp, vp, vp, vp, vp]
     _libs[path] = lib
     return lib
 
@@ -156,6 +179,30 @@ class ProvingKeyDevice:
     def free(self):
         if self.handle:
             self.ctx.lib.g16_pk_free(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class R1CSDevice:
+    """Device-resident sparse constraint system (g16_r1cs): the three matrices of `R1CS<F>`
+    (crates/groth16-r1cs) in CSR form, by constraint and by variable."""
+
+    def __init__(self, ctx: "Context", handle: int, num_constraints: int, num_variables: int):
+        self.ctx, self.handle = ctx, handle
+        self.num_constraints, self.num_variables = num_constraints, num_variables
+
+    @property
+    def domain_size(self) -> int:
+        return int(self.ctx.lib.g16_r1cs_domain_size(self.handle))
+
+    def free(self):
+        if self.handle:
+            self.ctx.lib.g16_r1cs_free(self.handle)
             self.handle = None
 
     def __del__(self):
@@ -361,4 +408,76 @@ class Context:
                                        _ptr(h_coeffs) if h_coeffs.shape[0] else None, h_coeffs.shape[0],
                                        _ptr(r), _ptr(s), _ptr(a), fl.ctypes.data, _ptr(b), fl.ctypes.data + 1,
                                        _ptr(c), fl.ctypes.data + 2))
+        return (a, int(fl[0])), (b, int(fl[1])), (c, int(fl[2]))
+
+    # ---- sparse R1CS: setup and prove for real circuits
+    def r1cs_upload(self, num_constraints: int, num_variables: int, a, b, c) -> R1CSDevice:
+        """a, b, c: (row_ptr[num_constraints + 1] uint32, col[nnz] uint32, val[nnz x 4] uint64 Montgomery Fr)."""
+        keep, structs = [], []
+        for row_ptr, col, val in (a, b, c):
+            row_ptr = np.ascontiguousarray(row_ptr, dtype=np.uint32)
+            col = np.ascontiguousarray(col, dtype=np.uint32)
+            val = _u64(val, 4)
+            if row_ptr.shape[0] != num_constraints + 1 or col.shape[0] != val.shape[0] or \
+                    (num_constraints and int(row_ptr[-1]) != col.shape[0]):
+                raise MSMError(G16_ERR_LENGTH, "CSR arrays are inconsistent")
+            keep += [row_ptr, col, val]
+            st = _Csr()
+            st.row_ptr, st.col, st.val = _ptr(row_ptr), _ptr(col) if col.shape[0] else None, _ptr(val) if col.shape[0] else None
+            structs.append(st)
+        h = ctypes.c_void_p()
+        self._check(self.lib.g16_r1cs_upload(self.handle, num_constraints, num_variables, ctypes.byref(structs[0]),
+                                             ctypes.byref(structs[1]), ctypes.byref(structs[2]), ctypes.byref(h)))
+        return R1CSDevice(self, h.value, num_constraints, num_variables)
+
+    def r1cs_domain_evals(self, r1cs: R1CSDevice, assignment):
+        """(<A-row i, w>, <B-row i, w>, <C-row i, w>) on the domain; three n x 4 uint64 arrays."""
+        w = _u64(assignment, 4)
+        n = r1cs.domain_size
+        out = [np.zeros((n, 4), dtype=np.uint64) for _ in range(3)]
+        self._check(self.lib.g16_r1cs_domain_evals(self.handle, r1cs.handle, _ptr(w), w.shape[0], *[_ptr(o) for o in out]))
+        return out
+
+    def r1cs_eval_at(self, r1cs: R1CSDevice, s):
+        """(A_j(s), B_j(s), C_j(s)) for every variable j; three num_variables x 4 uint64 arrays."""
+        s = _u64(s).reshape(4)
+        out = [np.zeros((r1cs.num_variables, 4), dtype=np.uint64) for _ in range(3)]
+        self._check(self.lib.g16_r1cs_eval_at(self.handle, r1cs.handle, _ptr(s), *[_ptr(o) for o in out]))
+        return out
+
+    def setup_crs(self, r1cs: R1CSDevice, params: dict, num_public: int, want_host: bool = True, want_device_pk: bool = False):
+        """CRS::generate_from_qap.  params: alpha, beta, gamma, delta, s as 4 x uint64 Montgomery limbs.
+        Returns (crs dict of host arrays or None, ProvingKeyDevice or None)."""
+        p = {k: _u64(params[k]).reshape(4) for k in ("alpha", "beta", "gamma", "delta", "s")}
+        nv, n = r1cs.num_variables, r1cs.domain_size
+        crs, st = None, None
+        if want_host:
+            n_ic = max(0, nv - num_public - 1)
+            crs = {"num_public": num_public}
+            st = _CrsHost()
+            for name, w in (("alpha_g1", 12), ("beta_g1", 12), ("delta_g1", 12), ("beta_g2", 24), ("gamma_g2", 24), ("delta_g2", 24)):
+                crs[name] = np.zeros(w, dtype=np.uint64)
+                setattr(st, name, _ptr(crs[name]))
+            for name, w, ln in (("a_g1", 12, nv), ("b_g1", 12, nv), ("b_g2", 24, nv), ("ic_g1", 12, n_ic),
+                                ("vk_ic_g1", 12, min(num_public + 1, nv)), ("h_g1", 12, n)):
+                crs[name] = np.zeros((ln, w), dtype=np.uint64)
+                crs[name + "_inf"] = np.zeros(ln, dtype=np.uint8)
+                setattr(st, name, _ptr(crs[name]) if ln else None)
+                setattr(st, name + "_inf", _ptr(crs[name + "_inf"]) if ln else None)
+        h = ctypes.c_void_p()
+        self._check(self.lib.g16_setup_crs(self.handle, r1cs.handle, _ptr(p["alpha"]), _ptr(p["beta"]), _ptr(p["gamma"]),
+                                           _ptr(p["delta"]), _ptr(p["s"]), num_public,
+                                           ctypes.byref(st) if st is not None else None,
+                                           ctypes.byref(h) if want_device_pk else None))
+        return crs, (ProvingKeyDevice(self, h.value) if want_device_pk else None)
+
+    def prove_r1cs(self, pk: ProvingKeyDevice, r1cs: R1CSDevice, assignment, r, s):
+        """Prover::prove from the un-truncated witness.  Returns ((a_xy, a_inf), (b_xy, b_inf), (c_xy, c_inf))."""
+        w = _u64(assignment, 4)
+        r = _u64(r).reshape(4)
+        s = _u64(s).reshape(4)
+        a = np.zeros(12, dtype=np.uint64); b = np.zeros(24, dtype=np.uint64); c = np.zeros(12, dtype=np.uint64)
+        fl = np.zeros(3, dtype=np.uint8)
+        self._check(self.lib.g16_prove_r1cs(self.handle, pk.handle, r1cs.handle, _ptr(w), w.shape[0], _ptr(r), _ptr(s),
+                                            _ptr(a), fl.ctypes.data, _ptr(b), fl.ctypes.data + 1, _ptr(c), fl.ctypes.data + 2))
         return (a, int(fl[0])), (b, int(fl[1])), (c, int(fl[2]))
