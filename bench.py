@@ -338,6 +338,16 @@ def main():
             "achieved": alg_imad / (acc_ms * 1e-3) / 1e12 if acc_ms else None,
             "kernel": "BucketAccumulate<Fq>", "kernel_ms": acc_ms, "traffic": None,
             "algorithmic": f"{FQ_MUL_PER_PAIR} Fq-mul/pair x {IMAD_PER_FQ_MUL} IMAD (SURVEY.md 8d)"}
+    # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set full capture of
+    # this exact configuration (profiles/r01_ncu_traffic.json); null for configurations never captured
+    try:
+        for cap in json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))["captures"]:
+            if (cap["log_n"], cap["window_bits"], cap["windows"]) == (args.log_n, int(plan[0]), int(plan[1])) and world == 1:
+                roof["traffic"] = cap["dram_bytes_read"] + cap["dram_bytes_write"]
+                roof["traffic_unit"] = "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)"
+                roof["algorithmic_bytes"] = cap["algorithmic_bytes"]
+    except (OSError, KeyError, ValueError):
+        pass
     if roof["achieved"] and roof["peak"]:
         roof["frac"] = roof["achieved"] / roof["peak"]
         roof["whole_step_frac"] = value / world * FQ_MUL_PER_PAIR * IMAD_PER_FQ_MUL / imad_peak_per_s

@@ -166,3 +166,19 @@ def test_large_msm_by_discrete_log(gpu_ctx, oracle, gens, log_n):
 
 def test_chunked_host_path(gpu_ctx, oracle, gens):
     pc.check_chunked_host_path(gpu_ctx, oracle, gens, 5000, 21)
+
+
+@pytest.mark.parametrize("rounds", [1, 3, 8])
+def test_affine_bucket_accumulation(gpu_ctx, oracle, gens, rounds):
+    """Bucket sums as trees of affine additions with block-shared inversions (csrc/affine_acc.cuh), forced on
+    for sizes the automatic choice leaves on the XYZZ walk: same group elements, all exceptional pairs."""
+    gpu_ctx.set_affine_rounds(rounds)
+    try:
+        pc.check_golden_msm(gpu_ctx)
+        pc.check_random_msm(gpu_ctx, oracle, gens, "g1", 20000, 31, windows=(0, 6, 11), pre=(9, 0))
+        pc.check_random_msm(gpu_ctx, oracle, gens, "g2", 3000, 32, windows=(0, 5), pre=(8,))
+        pc.check_adversarial(gpu_ctx, oracle, gens, "g1", 1 << 13, 33)
+        pc.check_adversarial(gpu_ctx, oracle, gens, "g2", 1 << 10, 34)
+        pc.check_skewed_scalars(gpu_ctx, oracle, gens, 3000, 35)
+    finally:
+        gpu_ctx.set_affine_rounds(-1)

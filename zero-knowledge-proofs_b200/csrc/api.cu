@@ -114,6 +114,12 @@ int g16_ctx_set_window_bits(g16_ctx *ctx, unsigned c) {
     return G16_OK;
 }
 
+int g16_ctx_set_affine_rounds(g16_ctx *ctx, int rounds) {
+    if (!ctx || rounds < -1 || rounds > (int)AFF_MAX_ROUNDS_API) return G16_ERR_INVALID;
+    affine_rounds_setting() = rounds;
+    return G16_OK;
+}
+
 // ---- bases ------------------------------------------------------------------------------
 extern "C++" {
 template <class F>

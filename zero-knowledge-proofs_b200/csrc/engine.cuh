@@ -13,13 +13,13 @@ enum Group { GROUP_G1 = 1, GROUP_G2 = 2 };
 template <class F> struct GroupOf { static constexpr int id = FieldWords<F>::group; };
 
 struct Workspace {
-    DevBuf scalars, counts, codes, ranks, bins, items, item_start, chunk_out, cursor, entries, buckets, red[6], scan_tmp, out, partials, staging;
+    DevBuf scalars, counts, codes, ranks, bins, items, item_start, chunk_out, cursor, entries, buckets, affine, red[6], scan_tmp, out, partials, staging;
     DevBuf prove_w, prove_misc, ntt_abc, ntt_tw, ntt_consts, ntt_out;
     uint32_t ntt_log_n = 0xffffffffu;   // size the cached twiddles / constants were built for (none yet)
     DevBuf fb_base, fb_powers, fb_table[3], fb_out, fb_flags;
     std::vector<uint32_t> fb_table_key[3];  // base limbs the cached table was built for
     void release() {
-        scalars.release(); counts.release(); codes.release(); ranks.release(); bins.release(); items.release(); item_start.release(); chunk_out.release(); cursor.release(); entries.release(); buckets.release();
+        scalars.release(); counts.release(); codes.release(); ranks.release(); bins.release(); items.release(); item_start.release(); chunk_out.release(); cursor.release(); entries.release(); buckets.release(); affine.release();
         for (auto &r : red) r.release();
         scan_tmp.release(); out.release(); partials.release(); staging.release();
         prove_w.release(); prove_misc.release(); ntt_abc.release(); ntt_tw.release(); ntt_consts.release(); ntt_out.release(); ntt_log_n = 0xffffffffu; fb_base.release(); fb_powers.release(); fb_out.release(); fb_flags.release();
@@ -200,6 +200,26 @@ inline unsigned choose_precompute_c(size_t n, size_t point_bytes, size_t budget)
     return best_c;
 }
 
+// Affine bucket accumulation (affine_acc.cuh): number of pairwise rounds before the XYZZ tail.  -1 = choose from
+// the size of the call: the shared inversions cost latency, not throughput, so the tree pays once there are
+// enough blocks to hide it; small calls keep the XYZZ walk.  Process-wide tuning knob (g16_ctx_set_affine_rounds,
+// or G16_AFFINE_ROUNDS in the environment for experiments).
+inline int &affine_rounds_setting() {
+    static int v = getenv("G16_AFFINE_ROUNDS") ? atoi(getenv("G16_AFFINE_ROUNDS")) : -1;
+    return v;
+}
+constexpr int AFF_MAX_ROUNDS_API = 8;
+constexpr size_t AFFINE_MIN_ENTRIES = (size_t)1 << 24;
+constexpr size_t AFFINE_MAX_ENTRIES = (size_t)1 << 28;   // scratch: ~96 B per entry
+constexpr uint32_t AFFINE_DEFAULT_ROUNDS = 3;
+inline uint32_t affine_rounds_for(size_t entries, size_t buckets) {
+    int v = affine_rounds_setting();
+    if (v >= 0) return (uint32_t)std::min<int>(v, 8);
+    if (entries < AFFINE_MIN_ENTRIES || entries > AFFINE_MAX_ENTRIES) return 0;
+    if (entries < 8 * buckets) return 0;   // nearly empty buckets: nothing to pair
+    return AFFINE_DEFAULT_ROUNDS;
+}
+
 constexpr uint32_t REDUCE_LOG_L = 5;
 constexpr size_t TILE_LEVEL_MAX = 1u << 16;   // levels with at most this many entries run block-cooperatively
 constexpr size_t THREAD_LEVEL_GROUPS = 1u << 16;   // groups a thread level aims to leave behind
@@ -280,7 +300,16 @@ void msm_run(Device &dv, const BasesShard &sh, const uint32_t *d_scalars, size_t
     // 4. bucket accumulation (the hot kernel) + fold of split buckets
     uint32_t *buckets = ws.buckets.as<uint32_t>(total * 4 * FieldWords<F>::N);
     uint32_t *chunk_out = ws.chunk_out.as<uint32_t>(max_split * 4 * FieldWords<F>::N);
-    k_accumulate<F>(s, max_items, pts, entries, items, bins + nbins, buckets, chunk_out);
+    uint32_t aff_rounds = affine_rounds_for(max_entries, total);
+    if (aff_rounds) {
+        // chunks of split buckets (the front of the item array) keep the XYZZ walk; every whole bucket is summed
+        // as a tree of affine additions with block-shared inversions (affine_acc.cuh)
+        uint32_t *scratch = ws.affine.as<uint32_t>(k_affine_scratch_words<F>(max_entries, total, aff_rounds));
+        k_accumulate<F>(s, max_split, pts, entries, items, bins + 1, buckets, chunk_out);
+        k_accumulate_affine<F>(s, total, pts, entries, items, bins + 1, bins + nbins, aff_rounds, scratch, max_entries, total, buckets);
+    } else {
+        k_accumulate<F>(s, max_items, pts, entries, items, bins + nbins, buckets, chunk_out);
+    }
     k_chunk_merge<F>(s, max_split_buckets, split_list, chunk_out, buckets);
     dv.timer.mark(4, s);
     // 5. parallel bucket reduction: thread levels while the level is work bound (every thread walks 2^log_l

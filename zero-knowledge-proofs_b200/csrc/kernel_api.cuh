@@ -47,6 +47,14 @@ void k_exclusive_scan(stream_t s, const uint32_t *in, uint32_t *out, size_t n, u
 template <class F>
 void k_accumulate(stream_t s, size_t max_items, const uint32_t *pts, const uint32_t *entries, const WorkItem *work,
                   const uint32_t *n_items, uint32_t *buckets, uint32_t *chunk_out);
+// bucket accumulation in affine coordinates with block-shared inversions (affine_acc.cuh): whole-bucket items
+// [*first_item, *n_items) of the item array; scratch holds k_affine_scratch_words<F>(...) words
+template <class F>
+size_t k_affine_scratch_words(size_t n_entries, size_t n_buckets, uint32_t rounds);
+template <class F>
+void k_accumulate_affine(stream_t s, size_t max_items, const uint32_t *pts, const uint32_t *entries, const WorkItem *work,
+                         const uint32_t *first_item, const uint32_t *n_items, uint32_t rounds, uint32_t *scratch,
+                         size_t n_entries, size_t n_buckets, uint32_t *buckets);
 template <class F>
 void k_chunk_merge(stream_t s, size_t max_split, const uint32_t *split_list, const uint32_t *chunk_out, uint32_t *buckets);
 template <class F>

@@ -3,6 +3,7 @@
 #include "kernel_api.cuh"
 #include "fixed_base_kernels.cuh"
 #include "msm_kernels.cuh"
+#include "affine_acc.cuh"
 
 namespace g16 {
 
@@ -10,6 +11,28 @@ template <class F>
 void k_accumulate(stream_t s, size_t max_items, const uint32_t *pts, const uint32_t *entries, const WorkItem *work,
                   const uint32_t *n_items, uint32_t *buckets, uint32_t *chunk_out) {
     launch<BucketAccumulate<F>>(max_items, s, pts, entries, work, n_items, buckets, chunk_out);
+}
+template <class F>
+size_t k_affine_scratch_words(size_t n_entries, size_t n_buckets, uint32_t rounds) {
+    size_t slots = 0;
+    for (uint32_t r = 0; r < rounds; ++r) slots += affine_round_slots(n_entries, n_buckets, r);
+    return slots * 2 * F::N;
+}
+template <class F>
+void k_accumulate_affine(stream_t s, size_t max_items, const uint32_t *pts, const uint32_t *entries, const WorkItem *work,
+                         const uint32_t *first_item, const uint32_t *n_items, uint32_t rounds, uint32_t *scratch,
+                         size_t n_entries, size_t n_buckets, uint32_t *buckets) {
+    if (max_items == 0) return;
+#ifndef G16_EMU
+    size_t blocks = (max_items + AFF_BLOCK - 1) / AFF_BLOCK;
+    size_t smem = (size_t)2 * AFF_BLOCK * F::N * sizeof(uint32_t);
+    accumulate_affine_kernel<F><<<(unsigned)blocks, AFF_BLOCK, smem, s>>>(pts, entries, work, first_item, n_items, rounds, scratch,
+                                                                         n_entries, n_buckets, buckets);
+    G16_CUDA_CHECK(cudaGetLastError());
+    note_launch();
+#else
+    launch<AccumulateAffineSerial<F>>(max_items, s, pts, entries, work, first_item, n_items, rounds, scratch, n_entries, n_buckets, buckets);
+#endif
 }
 template <class F>
 void k_chunk_merge(stream_t s, size_t max_split, const uint32_t *split_list, const uint32_t *chunk_out, uint32_t *buckets) {

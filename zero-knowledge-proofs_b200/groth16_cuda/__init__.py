@@ -31,7 +31,7 @@ G1_AFFINE_WORDS, G2_AFFINE_WORDS = 25, 49
 
 EXPORTS = [
     "g16_version", "g16_device_count", "g16_ctx_create", "g16_ctx_destroy", "g16_last_error",
-    "g16_ctx_set_stream", "g16_ctx_synchronize", "g16_ctx_set_window_bits",
+    "g16_ctx_set_stream", "g16_ctx_synchronize", "g16_ctx_set_window_bits", "g16_ctx_set_affine_rounds",
     "g16_g1_bases_upload", "g16_g2_bases_upload", "g16_g1_bases_from_device", "g16_g2_bases_from_device",
     "g16_bases_free", "g16_bases_len", "g16_bases_precompute",
     "g16_g1_msm", "g16_g2_msm", "g16_g1_msm_oneshot", "g16_g2_msm_oneshot",
@@ -99,6 +99,7 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.g16_ctx_set_stream.argtypes = [vp, vp]
     lib.g16_ctx_synchronize.argtypes = [vp]
     lib.g16_ctx_set_window_bits.argtypes = [vp, ctypes.c_uint]
+    lib.g16_ctx_set_affine_rounds.argtypes = [vp, ctypes.c_int]
     for g in ("g1", "g2"):
         getattr(lib, f"g16_{g}_bases_upload").argtypes = [vp, vp, vp, sz, ctypes.POINTER(vp)]
         getattr(lib, f"g16_{g}_bases_from_device").argtypes = [vp, vp, sz, ctypes.POINTER(vp)]
@@ -249,6 +250,10 @@ class Context:
 
     def set_window_bits(self, c: int):
         self._check(self.lib.g16_ctx_set_window_bits(self.handle, c))
+
+    def set_affine_rounds(self, rounds: int):
+        """Pairwise affine rounds of the bucket sums (-1 = auto, 0 = XYZZ walk only); process-wide tuning."""
+        self._check(self.lib.g16_ctx_set_affine_rounds(self.handle, rounds))
 
     # ---- bases
     def _upload(self, g: str, xy, inf) -> Bases:
