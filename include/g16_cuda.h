@@ -219,6 +219,30 @@ int g16_prove_r1cs(g16_ctx *ctx, const g16_pk *pk, const g16_r1cs *r1cs, const u
                    const uint64_t r[4], const uint64_t s[4], uint64_t a_xy[12], uint8_t *a_inf, uint64_t b_xy[24],
                    uint8_t *b_inf, uint64_t c_xy[12], uint8_t *c_inf);
 
+/* ---- wire format ------------------------------------------------------------------- */
+/* ark `CanonicalSerialize` / `CanonicalDeserialize` as ark-bls12-381 0.4.0 implements them for G1Affine and
+ * G2Affine (the Zcash encoding): Fq = 48 bytes big-endian canonical; G1 = x (compressed, 48 B) or x || y (96 B);
+ * G2 = x.c1 || x.c0 (96 B) or x.c1 || x.c0 || y.c1 || y.c0 (192 B); top bits of byte 0: 0x80 compressed, 0x40
+ * infinity, 0x20 "y is the larger root".  `Proof` (crates/groth16-core/src/lib.rs:27-36, derive
+ * CanonicalSerialize) = a || b || c = 192 bytes compressed / 384 uncompressed -- what `serialize_compressed` /
+ * `deserialize_compressed` of the reference's proof produce and accept.  The vector entry points are the batch
+ * form a key file needs (`Vec<G1Affine>` body; ark's u64 little-endian length prefix is the caller's).
+ * Deserialisation errors mirror ark's SerializationError: G16_ERR_INVALID with "UnexpectedFlags" (compression
+ * bit does not match) or "InvalidData" (coordinate >= q, no point with that x, or -- validate != 0, ark's
+ * Validate::Yes -- not in the prime-order subgroup); status (n bytes, may be NULL) receives 0 / 1 (InvalidData) /
+ * 2 (UnexpectedFlags) per element, rejected elements come back as the identity.  Uncompressed input is also
+ * checked against the curve equation when validate != 0.  Single-device contexts. */
+int g16_g1_serialize(g16_ctx *ctx, const uint64_t *xy, const uint8_t *inf, size_t n, int compressed, uint8_t *out);
+int g16_g2_serialize(g16_ctx *ctx, const uint64_t *xy, const uint8_t *inf, size_t n, int compressed, uint8_t *out);
+int g16_g1_deserialize(g16_ctx *ctx, const uint8_t *bytes, size_t n, int compressed, int validate, uint64_t *out_xy,
+                       uint8_t *out_inf, uint8_t *status);
+int g16_g2_deserialize(g16_ctx *ctx, const uint8_t *bytes, size_t n, int compressed, int validate, uint64_t *out_xy,
+                       uint8_t *out_inf, uint8_t *status);
+int g16_proof_serialize(g16_ctx *ctx, const uint64_t a_xy[12], uint8_t a_inf, const uint64_t b_xy[24], uint8_t b_inf,
+                        const uint64_t c_xy[12], uint8_t c_inf, int compressed, uint8_t *out);
+int g16_proof_deserialize(g16_ctx *ctx, const uint8_t *bytes, int compressed, int validate, uint64_t a_xy[12], uint8_t *a_inf,
+                          uint64_t b_xy[24], uint8_t *b_inf, uint64_t c_xy[12], uint8_t *c_inf);
+
 /* ---- test hooks (used by tests/ and bench.py only) ------------------------------------------ */
 /* kernels launched by the library since it was loaded */
 unsigned long long g16_launch_count(void);

@@ -375,6 +375,101 @@ def g1_decompress(b):
     return (x, y)
 
 
+def fq2_sqrt(a):
+    """a root of a in Fq[u]/(u^2+1) or None (complex method, q = 3 mod 4)."""
+    a0, a1 = a[0] % Q, a[1] % Q
+    if a1 == 0:
+        s = fq_sqrt(a0)
+        if s is not None:
+            return (s, 0)
+        s = fq_sqrt((-a0) % Q)
+        return None if s is None else (0, s)
+    alpha = fq_sqrt((a0 * a0 + a1 * a1) % Q)
+    if alpha is None:
+        return None
+    half = pow(2, -1, Q)
+    for delta in ((a0 + alpha) * half % Q, (a0 - alpha) * half % Q):
+        x0 = fq_sqrt(delta)
+        if x0 is not None and x0 != 0:
+            x1 = a1 * pow(2 * x0, -1, Q) % Q
+            if ((x0 * x0 - x1 * x1) % Q, 2 * x0 * x1 % Q) == (a0, a1):
+                return (x0, x1)
+    return None
+
+
+class WireError(ValueError):
+    """ark_serialize::SerializationError: .kind is "InvalidData" or "UnexpectedFlags"."""
+    def __init__(self, kind):
+        super().__init__(kind)
+        self.kind = kind
+
+
+def _read_fq(b, mask):
+    v = int.from_bytes(b, "big")
+    if mask:
+        v &= (1 << 381) - 1
+    if v >= Q:
+        raise WireError("InvalidData")
+    return v
+
+
+def _in_subgroup(curve, P):
+    """r * P == O by plain double-and-add (Curve.mul reduces the scalar mod r, which would beg the question)."""
+    acc = (curve.F.one, curve.F.one, curve.F.zero)
+    base = curve.to_jac(P)
+    for bit in bin(R)[2:]:
+        acc = curve.jac_double(acc)
+        if bit == '1':
+            acc = curve.jac_add(acc, base)
+    return curve.jac_is_zero(acc)
+
+
+def point_deserialize(group, b, compressed=True, validate=True):
+    """ark-bls12-381 0.4.0 read_g{1,2}_{compressed,uncompressed} + deserialize_with_mode [ark-memory]:
+    compression flag must match, infinity flag -> identity, coordinates canonical, y from the curve equation
+    with the sign flag; validate = Validate::Yes adds the subgroup check (and, here, the curve equation for
+    uncompressed input).  Returns the affine point or None (identity)."""
+    k = 1 if group == "g1" else 2
+    flags = b[0] >> 5
+    if bool(flags & 4) != bool(compressed):
+        raise WireError("UnexpectedFlags")
+    if flags & 2:
+        return None
+    curve = G1 if group == "g1" else G2
+    if group == "g1":
+        x = _read_fq(b[0:48], True)
+        rhs = (x * x * x + 4) % Q
+    else:
+        x1 = _read_fq(b[0:48], True)
+        x0 = _read_fq(b[48:96], False)
+        x = (x0, x1)
+        xx = Fq2Ops.mul(Fq2Ops.mul(x, x), x)
+        rhs = ((xx[0] + 4) % Q, (xx[1] + 4) % Q)
+    if compressed:
+        y = fq_sqrt(rhs) if group == "g1" else fq2_sqrt(rhs)
+        if y is None:
+            raise WireError("InvalidData")
+        largest = _fq_lex_largest(y) if group == "g1" else _fq2_lex_largest(y)
+        if largest != bool(flags & 1):
+            y = (Q - y) % Q if group == "g1" else ((Q - y[0]) % Q, (Q - y[1]) % Q)
+    else:
+        o = 48 * k
+        if group == "g1":
+            y = _read_fq(b[o:o + 48], False)
+            ok = y * y % Q == rhs
+        else:
+            y1 = _read_fq(b[o:o + 48], False)
+            y0 = _read_fq(b[o + 48:o + 96], False)
+            y = (y0, y1)
+            ok = Fq2Ops.mul(y, y) == rhs
+        if validate and not ok:
+            raise WireError("InvalidData")
+    P = (x, y)
+    if validate and not _in_subgroup(curve, P):
+        raise WireError("InvalidData")
+    return P
+
+
 def proof_bytes(a, b, c, compressed=True):
     if compressed:
         return g1_compress(a) + g2_compress(b) + g1_compress(c)

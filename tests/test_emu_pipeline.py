@@ -73,3 +73,13 @@ def test_emu_affine_bucket_accumulation(emu_ctx, oracle, gens):
             pc.check_skewed_scalars(emu_ctx, oracle, gens, 1500, 8)
         finally:
             emu_ctx.set_affine_rounds(-1)
+
+
+def test_emu_wire_format(emu_ctx):
+    import wire_cases as wc
+    wc.check_known_answers(emu_ctx)
+    wc.check_roundtrip(emu_ctx, "g1")
+    wc.check_roundtrip(emu_ctx, "g2", ks=wc.KS[:6])
+    wc.check_rejects(emu_ctx, "g1")
+    wc.check_rejects(emu_ctx, "g2")
+    wc.check_proof(emu_ctx)

@@ -182,3 +182,30 @@ def test_affine_bucket_accumulation(gpu_ctx, oracle, gens, rounds):
         pc.check_skewed_scalars(gpu_ctx, oracle, gens, 3000, 35)
     finally:
         gpu_ctx.set_affine_rounds(-1)
+
+
+def test_wire_format(gpu_ctx, oracle, gens):
+    """ark CanonicalSerialize / CanonicalDeserialize of G1Affine, G2Affine and Proof on the device."""
+    import wire_cases as wc
+    wc.check_known_answers(gpu_ctx)
+    wc.check_roundtrip(gpu_ctx, "g1")
+    wc.check_roundtrip(gpu_ctx, "g2")
+    wc.check_rejects(gpu_ctx, "g1")
+    wc.check_rejects(gpu_ctx, "g2")
+    wc.check_proof(gpu_ctx)
+    # batch: encode -> decode (with the subgroup check) is the identity on 2^13 CRS-style points, and the
+    # compressed form of the first elements matches the big-integer encoder
+    import bls12_381 as bls
+    for group, n in (("g1", 1 << 13), ("g2", 1 << 11)):
+        pts, inf = helpers.make_points(oracle, gens, group, 0x3e51a1, n)
+        pts[5] = 0; inf[5] = 1
+        for compressed in (True, False):
+            data = gpu_ctx.serialize_points(group, pts, inf, compressed=compressed)
+            xy, back_inf = gpu_ctx.deserialize_points(group, data, compressed=compressed, validate=True)
+            assert (xy == pts).all() and (back_inf == inf).all()
+        per = 48 if group == "g1" else 96
+        data = gpu_ctx.serialize_points(group, pts[:8], inf[:8])
+        for i in range(8):
+            p = (bls.g1_from_mont if group == "g1" else bls.g2_from_mont)([int(v) for v in pts[i]], int(inf[i]))
+            exp = bls.g1_compress(p) if group == "g1" else bls.g2_compress(p)
+            assert data[i * per:(i + 1) * per] == exp

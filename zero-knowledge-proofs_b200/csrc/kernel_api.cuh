@@ -111,6 +111,13 @@ void k_crs_exponents(stream_t s, size_t num_vars, const uint32_t *vals, const ui
 void k_crs_h_exponents(stream_t s, size_t n, const uint32_t *blk, uint32_t *h);
 void k_validate_row(stream_t s, const uint32_t *abc, uint32_t n, uint32_t *flag);
 
+// wire format (ark CanonicalSerialize of G1Affine / G2Affine), see wire_kernels.cuh
+constexpr uint8_t WIRE_STATUS_OK = 0, WIRE_STATUS_INVALID_DATA = 1, WIRE_STATUS_UNEXPECTED_FLAGS = 2;
+template <class F>
+void k_point_encode(stream_t s, size_t n, const uint32_t *pts, bool compressed, uint32_t *out_bytes);
+template <class F>
+void k_point_decode(stream_t s, size_t n, const uint32_t *in_bytes, bool compressed, bool validate, uint32_t *pts, uint8_t *status);
+
 // test hooks
 void k_debug_fq_op(stream_t s, size_t n, int op, const uint32_t *a, const uint32_t *b, uint32_t *out);
 void k_debug_fr_from_mont(stream_t s, size_t n, const uint32_t *a, uint32_t *out);

@@ -42,6 +42,8 @@ EXPORTS = [
     "g16_pk_upload", "g16_pk_free", "g16_prove", "g16_pk_precompute", "g16_quotient_h",
     "g16_r1cs_upload", "g16_r1cs_free", "g16_r1cs_domain_size", "g16_r1cs_domain_evals", "g16_r1cs_eval_at",
     "g16_setup_crs", "g16_prove_r1cs",
+    "g16_g1_serialize", "g16_g2_serialize", "g16_g1_deserialize", "g16_g2_deserialize",
+    "g16_proof_serialize", "g16_proof_deserialize",
 ]
 
 
@@ -130,6 +132,12 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.g16_r1cs_eval_at.argtypes = [vp, vp, vp, vp, vp, vp]
     lib.g16_setup_crs.argtypes = [vp, vp, vp, vp, vp, vp, vp, sz, ctypes.POINTER(_CrsHost), ctypes.POINTER(vp)]
     lib.g16_prove_r1cs.argtypes = [vp, vp, vp, vp, sz, vp, vp, vp, vp, vp, vp, vp, vp]
+    u8 = ctypes.c_uint8
+    for g in ("g1", "g2"):
+        getattr(lib, f"g16_{g}_serialize").argtypes = [vp, vp, vp, sz, ci, vp]
+        getattr(lib, f"g16_{g}_deserialize").argtypes = [vp, vp, sz, ci, ci, vp, vp, vp]
+    lib.g16_proof_serialize.argtypes = [vp, vp, u8, vp, u8, vp, u8, ci, vp]
+    lib.g16_proof_deserialize.argtypes = [vp, vp, ci, ci, vp, vp, vp, vp, vp, vp]
     _libs[path] = lib
     return lib
 
@@ -413,6 +421,60 @@ class Context:
                                        _ptr(h_coeffs) if h_coeffs.shape[0] else None, h_coeffs.shape[0],
                                        _ptr(r), _ptr(s), _ptr(a), fl.ctypes.data, _ptr(b), fl.ctypes.data + 1,
                                        _ptr(c), fl.ctypes.data + 2))
+        return (a, int(fl[0])), (b, int(fl[1])), (c, int(fl[2]))
+
+    # ---- wire format: ark CanonicalSerialize / CanonicalDeserialize (Zcash encoding of ark-bls12-381)
+    def serialize_points(self, group: str, points_xy, points_inf=None, compressed: bool = True) -> bytes:
+        """Concatenated encodings of a `Vec<G1Affine>` / `Vec<G2Affine>` body (no length prefix)."""
+        width = G1_WORDS64 if group == "g1" else G2_WORDS64
+        xy = _u64(points_xy, width)
+        n = xy.shape[0]
+        inf = None if points_inf is None else np.ascontiguousarray(points_inf, dtype=np.uint8)
+        per = (48 if compressed else 96) * (1 if group == "g1" else 2)
+        out = np.zeros(n * per, dtype=np.uint8)
+        f = getattr(self.lib, f"g16_{group}_serialize")
+        self._check(f(self.handle, _ptr(xy) if n else None, _ptr(inf), n, int(compressed), _ptr(out) if n else None))
+        return out.tobytes()
+
+    def deserialize_points(self, group: str, data: bytes, compressed: bool = True, validate: bool = True,
+                           return_status: bool = False):
+        """Inverse of serialize_points.  Raises MSMError ("InvalidData ..." / "UnexpectedFlags ...") like ark's
+        SerializationError unless return_status, in which case (xy, inf, status) comes back for every element."""
+        width = G1_WORDS64 if group == "g1" else G2_WORDS64
+        per = (48 if compressed else 96) * (1 if group == "g1" else 2)
+        if len(data) % per:
+            raise MSMError(G16_ERR_LENGTH, "InvalidData: truncated input")
+        n = len(data) // per
+        buf = np.frombuffer(data, dtype=np.uint8).copy()
+        xy = np.zeros((n, width), dtype=np.uint64)
+        inf = np.zeros(n, dtype=np.uint8)
+        status = np.zeros(n, dtype=np.uint8)
+        f = getattr(self.lib, f"g16_{group}_deserialize")
+        rc = f(self.handle, _ptr(buf) if n else None, n, int(compressed), int(validate), _ptr(xy) if n else None,
+               _ptr(inf), _ptr(status))
+        if return_status and rc in (G16_OK, G16_ERR_INVALID):
+            return xy, inf, status
+        self._check(rc)
+        return xy, inf
+
+    def proof_serialize(self, a, b, c, compressed: bool = True) -> bytes:
+        """`Proof::serialize_compressed` / `serialize_uncompressed` (crates/groth16-core/src/lib.rs:27-36): a, b, c as
+        (xy, inf) pairs, the shape Context.prove returns.  192 / 384 bytes."""
+        (a_xy, a_inf), (b_xy, b_inf), (c_xy, c_inf) = a, b, c
+        a_xy, b_xy, c_xy = _u64(a_xy).reshape(12), _u64(b_xy).reshape(24), _u64(c_xy).reshape(12)
+        out = np.zeros(192 if compressed else 384, dtype=np.uint8)
+        self._check(self.lib.g16_proof_serialize(self.handle, _ptr(a_xy), int(a_inf), _ptr(b_xy), int(b_inf), _ptr(c_xy),
+                                                 int(c_inf), int(compressed), _ptr(out)))
+        return out.tobytes()
+
+    def proof_deserialize(self, data: bytes, compressed: bool = True, validate: bool = True):
+        if len(data) != (192 if compressed else 384):
+            raise MSMError(G16_ERR_LENGTH, "InvalidData: a proof is 192 bytes compressed, 384 uncompressed")
+        buf = np.frombuffer(data, dtype=np.uint8).copy()
+        a = np.zeros(12, dtype=np.uint64); b = np.zeros(24, dtype=np.uint64); c = np.zeros(12, dtype=np.uint64)
+        fl = np.zeros(3, dtype=np.uint8)
+        self._check(self.lib.g16_proof_deserialize(self.handle, _ptr(buf), int(compressed), int(validate), _ptr(a),
+                                                   fl.ctypes.data, _ptr(b), fl.ctypes.data + 1, _ptr(c), fl.ctypes.data + 2))
         return (a, int(fl[0])), (b, int(fl[1])), (c, int(fl[2]))
 
     # ---- sparse R1CS: setup and prove for real circuits
