@@ -1,40 +1,42 @@
-// Bucket accumulation in AFFINE coordinates with block-shared inversions (Montgomery's trick).
+// Bucket accumulation in AFFINE coordinates with shared inversions (Montgomery's trick).
 //
 // Replaces the same N * W mixed additions of ark-ec 0.4.2 `msm_bigint_wnaf`
 // (/root/reference/crates/groth16-core/src/lib.rs:282,296) as BucketAccumulate (msm_kernels.cuh); the
 // bucket sums are the same group elements, so everything downstream is unchanged.
 //
 // An affine addition costs one inversion, two multiplications and a squaring.  When the inversions of many
-// independent additions are shared (3 multiplications each plus ONE inversion for the whole batch) the
-// price is 5M + 1S = 6 field multiplications instead of the 8M + 2S = 10 of the XYZZ mixed addition the
-// hot kernel is bound by.  Independent additions come from summing a bucket as a TREE:
+// independent additions are shared (3 multiplications each plus ONE inversion per batch) the price is
+// 5M + 1S = 6 field multiplications instead of the 8M + 2S = 10 of the XYZZ mixed addition the hot kernel is
+// bound by.  Independent additions come from summing a bucket as a TREE:
 //
 //   round 0   entries (e0 e1)(e2 e3)...    gathered from the base table, signs applied  -> buf[0]
 //   round r   points of buf[r-1] pairwise                                                -> buf[r]
 //   tail      what is left after `rounds` rounds (len / 2^rounds points) joins an XYZZ accumulator
 //
-// One thread owns one work item (a whole bucket; the chunks of split buckets stay on the XYZZ kernel) and
-// walks its pairs twice per round:
-//   phase 1   d_j = x2 - x1 of every pair, running product; the product *before* d_j is parked in the
-//             first half of output slot j
-//   block     the 128 running products of the block are multiplied up a shared-memory tree, thread 0
-//             inverts the root (binary extended Euclid, fp.cuh), the inverses come back down the tree:
-//             one inversion per (block, round) = per several thousand additions.  Other resident blocks
-//             keep the multiplier busy meanwhile.
-//   phase 2   backwards: 1/d_j = inv_run * prefix_j, inv_run *= d_j, lambda = (y2 - y1) / d_j,
-//             x3 = lambda^2 - x1 - x2, y3 = lambda (x1 - x3) - y1   -> output slot j
-// Exceptional pairs (an operand at infinity, P + P, P - P) contribute d = 1 (or 2 y for a doubling) so the
-// shared product never vanishes, and are resolved in phase 2.
+// One thread owns one work item (a whole bucket; the chunks of split buckets stay on the XYZZ kernel).  A round
+// is three launches of independent threads -- no barriers, small kernels, registers per phase:
+//   AffinePhase1   d_j = x2 - x1 of every pair of the item, running product; the product *before* d_j is parked
+//                  in the first half of output slot j; the item's total goes to totals[item]
+//   BatchInverse   totals[] -> 1 / totals[] in groups of AFF_INV_GROUP (Montgomery's trick again: one
+//                  inversion per group = per several thousand additions)
+//   AffinePhase2   backwards: 1/d_j = inv_run * prefix_j, inv_run *= d_j, lambda = (y2 - y1) / d_j,
+//                  x3 = lambda^2 - x1 - x2, y3 = lambda (x1 - x3) - y1   -> output slot j
+// Exceptional pairs (an operand at infinity, P + P, P - P) contribute d = 1 (or 2 y for a doubling) so no
+// product ever vanishes, and are resolved in phase 2.
 //
 // Scratch layout: round r of the item with bucket number g writes slots [o_r, o_r + ceil(len_r / 2)) of
 // buf[r], o_0 = begin / 2 + g, o_r = o_(r-1) / 2 + g -- monotone in g with gaps >= the slot count, so no
 // offsets have to be scanned; buf[r] holds entries / 2^(r+1) + (2 - 2^-r) * buckets + 1 slots.
+//
+// (A first version ran all rounds in ONE kernel with a block-wide product tree and one inverting thread per
+// block: bit-exact but slower than the XYZZ walk -- barrier waits, instruction-cache misses of the large
+// kernel and 1.25 independent multiplications per thread left the multiplier 59 % busy;
+// profiles/r01_run13_affine_block_kernel.md.)
 #pragma once
 #include "msm_kernels.cuh"
 
 namespace g16 {
 
-constexpr int AFF_BLOCK = 128;
 constexpr uint32_t AFF_MAX_ROUNDS = 8;
 
 // slots of round-r scratch buffers, and their sum, for `entries` sorted entries over `buckets` buckets
@@ -121,25 +123,25 @@ struct AffineAcc {
         d = F::one();
         return CANCEL;
     }
-    // denominator of pair (pos, pos + 1) from the x coordinates alone whenever that decides the case
-    G16_HD static F pair_denominator(const Src &s, size_t pos) {
-        F x1 = load_x(s, pos), x2 = load_x(s, pos + 1);
-        F d = F::sub(x2, x1);
-        if (d.is_zero() || x1.is_zero() || x2.is_zero()) {
-            Affine<F> p = load(s, pos), q = load(s, pos + 1);
-            pair_case(p, q, d);
-        }
-        return d;
-    }
-
     // phase 1: product of the m denominators of pairs (src + 2 j, src + 2 j + 1); the product before pair j is
     // parked in slot dst_off + j
     G16_HD static F phase1(const Src &s, size_t src_off, uint32_t m, uint32_t *dst, size_t dst_off) {
         F run = F::one();
+        if (m == 0) return run;
+        // the x coordinates of the next pair are requested before the multiplication of this one
+        F x1 = load_x(s, src_off), x2 = load_x(s, src_off + 1);
         for (uint32_t j = 0; j < m; ++j) {
-            F d = pair_denominator(s, src_off + 2 * (size_t)j);
+            size_t pos = src_off + 2 * (size_t)j;
+            F nx1 = x1, nx2 = x2;
+            if (j + 1 < m) { nx1 = load_x(s, pos + 2); nx2 = load_x(s, pos + 3); }
+            F d = F::sub(x2, x1);
+            if (d.is_zero() || x1.is_zero() || x2.is_zero()) {
+                Affine<F> p = load(s, pos), q = load(s, pos + 1);
+                pair_case(p, q, d);
+            }
             store_f(dst, dst_off + j, run);
             run = F::mul(run, d);
+            x1 = nx1; x2 = nx2;
         }
         return run;
     }
@@ -182,111 +184,102 @@ struct AffineAcc {
     }
 };
 
-#if !defined(G16_EMU) && defined(__CUDACC__)
-// 1 / v for every thread of the block (v != 0).  tree: 2 * AFF_BLOCK field elements of shared memory.
+// Position of an item in round r: source (len, off) and destination slot o of that round.
 template <class F>
-__device__ __forceinline__ F block_inverse(uint32_t *tree, const F &v) {
-    constexpr int B = AFF_BLOCK, W = F::N;
-    const int t = threadIdx.x;
-    auto put = [&](int node, const F &x) {
-        const uint32_t *s = limbs(x);
-#pragma unroll
-        for (int k = 0; k < W; ++k) tree[(size_t)node * W + k] = s[k];
-    };
-    auto get = [&](int node) {
-        F x;
-        uint32_t *d = limbs(x);
-#pragma unroll
-        for (int k = 0; k < W; ++k) d[k] = tree[(size_t)node * W + k];
-        return x;
-    };
-    put(B + t, v);
-    __syncthreads();
-#pragma unroll 1
-    for (int s = B >> 1; s >= 1; s >>= 1) {
-        if (t < s) put(s + t, F::mul(get(2 * (s + t)), get(2 * (s + t) + 1)));
-        __syncthreads();
-    }
-    if (t == 0) put(1, field_inv_call(get(1)));
-    __syncthreads();
-#pragma unroll 1
-    for (int s = 1; s < B; s <<= 1) {
-        if (t < s) {
-            int i = s + t;
-            F inv = get(i), l = get(2 * i), r = get(2 * i + 1);
-            put(2 * i, F::mul(inv, r));
-            put(2 * i + 1, F::mul(inv, l));
-        }
-        __syncthreads();
-    }
-    F out = get(B + t);
-    __syncthreads();   // the tree is reused by the next round
-    return out;
-}
-
+struct AffGeom {
+    uint32_t len;
+    size_t off, o;
+    typename AffineAcc<F>::Src src;
+    uint32_t *dst;
+};
 template <class F>
-__global__ void __launch_bounds__(AFF_BLOCK) accumulate_affine_kernel(const uint32_t *pts, const uint32_t *entries,
-                                                                      const WorkItem *items, const uint32_t *first_item,
-                                                                      const uint32_t *n_items, uint32_t rounds,
-                                                                      uint32_t *scratch, size_t n_entries, size_t n_buckets,
-                                                                      uint32_t *buckets) {
-    extern __shared__ uint32_t tree[];
-    using A = AffineAcc<F>;
-    const size_t t = (size_t)blockIdx.x * AFF_BLOCK + threadIdx.x + *first_item;
-    const bool live = t < *n_items;
-    WorkItem it = live ? items[t] : WorkItem{0u, 0u, 0u};
-    uint32_t len = it.end - it.begin;
-    size_t off = it.begin;
-    typename A::Src src{pts, entries};
-    uint32_t *buf = scratch;
+G16_HD AffGeom<F> affine_geometry(const WorkItem &it, uint32_t r, const uint32_t *pts, const uint32_t *entries,
+                                  uint32_t *scratch, size_t n_entries, size_t n_buckets) {
+    AffGeom<F> g;
+    g.len = it.end - it.begin;
+    g.off = it.begin;
+    g.src = typename AffineAcc<F>::Src{pts, entries};
+    g.dst = scratch;
     size_t slots = n_entries / 2 + n_buckets + 1;
-#pragma unroll 1
-    for (uint32_t r = 0; r < rounds; ++r) {
-        if (!__syncthreads_or(len > 1)) break;
-        size_t o = off / 2 + it.bucket;
-        F run = A::phase1(src, off, len >> 1, buf, o);
-        F inv = block_inverse<F>(tree, run);
-        A::phase2(src, off, len, buf, o, inv);
-        len = (len + 1) >> 1;
-        off = o;
-        src = typename A::Src{buf, nullptr};
-        buf += slots * (2 * F::N);
+    for (uint32_t k = 0; k < r; ++k) {
+        g.off = g.off / 2 + it.bucket;
+        g.len = (g.len + 1) >> 1;
+        g.src = typename AffineAcc<F>::Src{g.dst, nullptr};
+        g.dst += slots * (2 * F::N);
         slots = slots / 2 + n_buckets + 1;
     }
-    if (!live) return;
-    XYZZ<F> acc = A::tail(src, off, len);
-    store_xyzz<F>(buckets, it.bucket, acc);
+    g.o = g.off / 2 + it.bucket;
+    return g;
 }
-#endif
 
-// Serial statement of the same schedule (host emulation build): every item runs its rounds on its own, with
-// its own inversion -- same slots, same sums.
+constexpr uint32_t AFF_INV_GROUP = 32;
+
+// one thread per slot of the item array behind *first_item (dead slots contribute 1 to their inversion group)
 template <class F>
-struct AccumulateAffineSerial {
-    static constexpr int BLOCK = 32;
+struct AffinePhase1 {
+    static constexpr int BLOCK = 128;
     G16_HD static void run(size_t t0, const uint32_t *pts, const uint32_t *entries, const WorkItem *items,
-                           const uint32_t *first_item, const uint32_t *n_items, uint32_t rounds, uint32_t *scratch,
-                           size_t n_entries, size_t n_buckets, uint32_t *buckets) {
+                           const uint32_t *first_item, const uint32_t *n_items, uint32_t r, uint32_t *scratch,
+                           size_t n_entries, size_t n_buckets, uint32_t *totals) {
+        using A = AffineAcc<F>;
+        size_t t = t0 + *first_item;
+        F run = F::one();
+        if (t < *n_items) {
+            AffGeom<F> g = affine_geometry<F>(items[t], r, pts, entries, scratch, n_entries, n_buckets);
+            run = A::phase1(g.src, g.off, g.len >> 1, g.dst, g.o);
+        }
+        A::store_f(totals, t0, run);   // totals: one field element per 2 * F::N words (slot layout)
+    }
+};
+
+// totals[i] <- 1 / totals[i] for i < n, AFF_INV_GROUP consecutive elements per thread and inversion
+template <class F>
+struct BatchInverse {
+    static constexpr int BLOCK = 64;
+    G16_HD static void run(size_t t, uint32_t *totals, size_t n) {
+        using A = AffineAcc<F>;
+        size_t lo = t * AFF_INV_GROUP, hi = lo + AFF_INV_GROUP < n ? lo + AFF_INV_GROUP : n;
+        F run = F::one();
+        for (size_t i = lo; i < hi; ++i) {
+            F v = A::load_f(totals, i);
+            A::store_f(totals + F::N, i, run);   // second half of the slot: product of the earlier elements
+            run = F::mul(run, v);
+        }
+        F inv = field_inv_call(run);
+        for (size_t i = hi; i-- > lo;) {
+            F v = A::load_f(totals, i);
+            A::store_f(totals, i, F::mul(inv, A::load_f(totals + F::N, i)));
+            inv = F::mul(inv, v);
+        }
+    }
+};
+
+template <class F>
+struct AffinePhase2 {
+    static constexpr int BLOCK = 128;
+    G16_HD static void run(size_t t0, const uint32_t *pts, const uint32_t *entries, const WorkItem *items,
+                           const uint32_t *first_item, const uint32_t *n_items, uint32_t r, uint32_t *scratch,
+                           size_t n_entries, size_t n_buckets, const uint32_t *totals) {
         using A = AffineAcc<F>;
         size_t t = t0 + *first_item;
         if (t >= *n_items) return;
+        AffGeom<F> g = affine_geometry<F>(items[t], r, pts, entries, scratch, n_entries, n_buckets);
+        A::phase2(g.src, g.off, g.len, g.dst, g.o, A::load_f(totals, t0));
+    }
+};
+
+// what the rounds left of every item joins an XYZZ accumulator (the form the bucket reduction consumes)
+template <class F>
+struct AffineTail {
+    static constexpr int BLOCK = 128;
+    G16_HD static void run(size_t t0, const uint32_t *pts, const uint32_t *entries, const WorkItem *items,
+                           const uint32_t *first_item, const uint32_t *n_items, uint32_t rounds, uint32_t *scratch,
+                           size_t n_entries, size_t n_buckets, uint32_t *buckets) {
+        size_t t = t0 + *first_item;
+        if (t >= *n_items) return;
         WorkItem it = items[t];
-        uint32_t len = it.end - it.begin;
-        size_t off = it.begin;
-        typename A::Src src{pts, entries};
-        uint32_t *buf = scratch;
-        size_t slots = n_entries / 2 + n_buckets + 1;
-        for (uint32_t r = 0; r < rounds && len > 1; ++r) {
-            size_t o = off / 2 + it.bucket;
-            F run = A::phase1(src, off, len >> 1, buf, o);
-            A::phase2(src, off, len, buf, o, F::inv(run));
-            len = (len + 1) >> 1;
-            off = o;
-            src = typename A::Src{buf, nullptr};
-            buf += slots * (2 * F::N);
-            slots = slots / 2 + n_buckets + 1;
-        }
-        XYZZ<F> acc = A::tail(src, off, len);
+        AffGeom<F> g = affine_geometry<F>(it, rounds, pts, entries, scratch, n_entries, n_buckets);
+        XYZZ<F> acc = AffineAcc<F>::tail(g.src, g.off, g.len);
         store_xyzz<F>(buckets, it.bucket, acc);
     }
 };

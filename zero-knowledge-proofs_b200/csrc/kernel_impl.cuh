@@ -14,7 +14,7 @@ void k_accumulate(stream_t s, size_t max_items, const uint32_t *pts, const uint3
 }
 template <class F>
 size_t k_affine_scratch_words(size_t n_entries, size_t n_buckets, uint32_t rounds) {
-    size_t slots = 0;
+    size_t slots = n_buckets + AFF_INV_GROUP;   // totals (+ prefix products of the batch inversion)
     for (uint32_t r = 0; r < rounds; ++r) slots += affine_round_slots(n_entries, n_buckets, r);
     return slots * 2 * F::N;
 }
@@ -23,16 +23,15 @@ void k_accumulate_affine(stream_t s, size_t max_items, const uint32_t *pts, cons
                          const uint32_t *first_item, const uint32_t *n_items, uint32_t rounds, uint32_t *scratch,
                          size_t n_entries, size_t n_buckets, uint32_t *buckets) {
     if (max_items == 0) return;
-#ifndef G16_EMU
-    size_t blocks = (max_items + AFF_BLOCK - 1) / AFF_BLOCK;
-    size_t smem = (size_t)2 * AFF_BLOCK * F::N * sizeof(uint32_t);
-    accumulate_affine_kernel<F><<<(unsigned)blocks, AFF_BLOCK, smem, s>>>(pts, entries, work, first_item, n_items, rounds, scratch,
-                                                                         n_entries, n_buckets, buckets);
-    G16_CUDA_CHECK(cudaGetLastError());
-    note_launch();
-#else
-    launch<AccumulateAffineSerial<F>>(max_items, s, pts, entries, work, first_item, n_items, rounds, scratch, n_entries, n_buckets, buckets);
-#endif
+    uint32_t *totals = scratch;                                         // max_items slots
+    uint32_t *bufs = scratch + (n_buckets + AFF_INV_GROUP) * 2 * F::N;   // round buffers
+    for (uint32_t r = 0; r < rounds; ++r) {
+        launch<AffinePhase1<F>>(max_items, s, pts, entries, work, first_item, n_items, r, bufs, n_entries, n_buckets, totals);
+        launch<BatchInverse<F>>((max_items + AFF_INV_GROUP - 1) / AFF_INV_GROUP, s, totals, max_items);
+        launch<AffinePhase2<F>>(max_items, s, pts, entries, work, first_item, n_items, r, bufs, n_entries, n_buckets,
+                                (const uint32_t *)totals);
+    }
+    launch<AffineTail<F>>(max_items, s, pts, entries, work, first_item, n_items, rounds, bufs, n_entries, n_buckets, buckets);
 }
 template <class F>
 void k_chunk_merge(stream_t s, size_t max_split, const uint32_t *split_list, const uint32_t *chunk_out, uint32_t *buckets) {
