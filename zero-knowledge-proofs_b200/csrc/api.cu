@@ -46,6 +46,9 @@ int g16_ctx_create(const int *devices, int ndev, g16_ctx **out) {
             d.id = id;
 #ifndef G16_EMU
             G16_CUDA_CHECK(cudaSetDevice(id));
+            // The point gathers of the bucket kernels touch 96-byte records at random; the default L2 fetch
+            // granularity pulls whole 128-byte lines from DRAM (measured: 200 B per 96-byte point).  A hint, per device.
+            if (const char *g = getenv("G16_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g));
             G16_CUDA_CHECK(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
             d.own_stream = true;
 #endif

@@ -27,7 +27,14 @@ void k_accumulate_affine(stream_t s, size_t max_items, const uint32_t *pts, cons
     uint32_t *bufs = scratch + (n_buckets + AFF_INV_GROUP) * 2 * F::N;   // round buffers
     for (uint32_t r = 0; r < rounds; ++r) {
         launch<AffinePhase1<F>>(max_items, s, pts, entries, work, first_item, n_items, r, bufs, n_entries, n_buckets, totals);
+#ifndef G16_EMU
+        size_t inv_threads = (max_items + AFF_INV_GROUP - 1) / AFF_INV_GROUP;
+        batch_inverse_kernel<F><<<(unsigned)((inv_threads + 63) / 64), 64, 0, s>>>(totals, max_items);
+        G16_CUDA_CHECK(cudaGetLastError());
+        note_launch();
+#else
         launch<BatchInverse<F>>((max_items + AFF_INV_GROUP - 1) / AFF_INV_GROUP, s, totals, max_items);
+#endif
         launch<AffinePhase2<F>>(max_items, s, pts, entries, work, first_item, n_items, r, bufs, n_entries, n_buckets,
                                 (const uint32_t *)totals);
     }

@@ -33,6 +33,11 @@ extern "C" {
     fn g16_g2_msm_oneshot(ctx: *mut RawCtx, xy: *const u64, inf: *const u8, scalars: *const u64, n: usize, out_xy: *mut u64, out_inf: *mut u8) -> c_int;
     fn g16_g1_fixed_base_mul(ctx: *mut RawCtx, base_xy: *const u64, scalars: *const u64, n: usize, out_xy: *mut u64, out_inf: *mut u8) -> c_int;
     fn g16_g2_fixed_base_mul(ctx: *mut RawCtx, base_xy: *const u64, scalars: *const u64, n: usize, out_xy: *mut u64, out_inf: *mut u8) -> c_int;
+    fn g16_quotient_h(ctx: *mut RawCtx, a: *const u64, b: *const u64, c: *const u64, n: usize, h: *mut u64) -> c_int;
+    fn g16_g1_serialize(ctx: *mut RawCtx, xy: *const u64, inf: *const u8, n: usize, compressed: c_int, out: *mut u8) -> c_int;
+    fn g16_g2_serialize(ctx: *mut RawCtx, xy: *const u64, inf: *const u8, n: usize, compressed: c_int, out: *mut u8) -> c_int;
+    fn g16_g1_deserialize(ctx: *mut RawCtx, bytes: *const u8, n: usize, compressed: c_int, validate: c_int, out_xy: *mut u64, out_inf: *mut u8, status: *mut u8) -> c_int;
+    fn g16_g2_deserialize(ctx: *mut RawCtx, bytes: *const u8, n: usize, compressed: c_int, validate: c_int, out_xy: *mut u64, out_inf: *mut u8, status: *mut u8) -> c_int;
 }
 
 /// One engine context (one or more GPUs of one box).  `!Sync`: one caller at a time, like the
@@ -156,6 +161,56 @@ pub fn fixed_base_mul_g2(ctx: &Context, base: &G2Affine, scalars: &[Fr]) -> Resu
     let rc = unsafe { g16_g2_fixed_base_mul(ctx.raw, bxy.as_ptr(), sc.as_ptr(), scalars.len(), out.as_mut_ptr(), inf.as_mut_ptr()) };
     if rc != 0 { return Err(err(ctx.raw, rc)); }
     Ok((0..scalars.len()).map(|i| g2_from(&out[24 * i..24 * i + 24], inf[i])).collect())
+}
+
+// ---- quotient polynomial (the stage that feeds the H MSM) ---------------------------------------------------
+/// `QAP::compute_quotient_polynomial` (`crates/groth16-qap/src/lib.rs:225-271`) from the domain evaluations of
+/// A, B, C (`n` = power of two): coefficients of H, `Err("Polynomial division failed")` like the reference.
+pub fn quotient_h(ctx: &Context, a: &[Fr], b: &[Fr], c: &[Fr]) -> Result<Vec<Fr>, String> {
+    let n = a.len();
+    if b.len() != n || c.len() != n { return Err("length mismatch".into()); }
+    let (pa, pb, pc) = (pack_scalars(a), pack_scalars(b), pack_scalars(c));
+    let mut out = vec![0u64; 4 * n];
+    let rc = unsafe { g16_quotient_h(ctx.raw, pa.as_ptr(), pb.as_ptr(), pc.as_ptr(), n, out.as_mut_ptr()) };
+    if rc != 0 { return Err(err(ctx.raw, rc)); }
+    Ok((0..n).map(|i| Fp(BigInt([out[4 * i], out[4 * i + 1], out[4 * i + 2], out[4 * i + 3]]), PhantomData)).collect())
+}
+
+// ---- wire format: the bytes `CanonicalSerialize` writes for Vec<G1Affine> / Vec<G2Affine> bodies ------------
+/// Same bytes as `for p in points { p.serialize_with_mode(&mut w, compress) }` (ark-bls12-381's Zcash encoding).
+pub fn serialize_g1(ctx: &Context, points: &[G1Affine], compressed: bool) -> Result<Vec<u8>, String> {
+    let (xy, inf) = pack_g1(points);
+    let mut out = vec![0u8; points.len() * if compressed { 48 } else { 96 }];
+    let rc = unsafe { g16_g1_serialize(ctx.raw, xy.as_ptr(), inf.as_ptr(), points.len(), compressed as c_int, out.as_mut_ptr()) };
+    if rc != 0 { return Err(err(ctx.raw, rc)); }
+    Ok(out)
+}
+pub fn serialize_g2(ctx: &Context, points: &[G2Affine], compressed: bool) -> Result<Vec<u8>, String> {
+    let (xy, inf) = pack_g2(points);
+    let mut out = vec![0u8; points.len() * if compressed { 96 } else { 192 }];
+    let rc = unsafe { g16_g2_serialize(ctx.raw, xy.as_ptr(), inf.as_ptr(), points.len(), compressed as c_int, out.as_mut_ptr()) };
+    if rc != 0 { return Err(err(ctx.raw, rc)); }
+    Ok(out)
+}
+/// `G1Affine::deserialize_with_mode(.., compress, validate)` per element; `Err("InvalidData ..")` /
+/// `Err("UnexpectedFlags ..")` name the first rejected element like ark's SerializationError.
+pub fn deserialize_g1(ctx: &Context, bytes: &[u8], compressed: bool, validate: bool) -> Result<Vec<G1Affine>, String> {
+    let per = if compressed { 48 } else { 96 };
+    if bytes.len() % per != 0 { return Err("InvalidData: truncated input".into()); }
+    let n = bytes.len() / per;
+    let (mut out, mut inf) = (vec![0u64; 12 * n], vec![0u8; n]);
+    let rc = unsafe { g16_g1_deserialize(ctx.raw, bytes.as_ptr(), n, compressed as c_int, validate as c_int, out.as_mut_ptr(), inf.as_mut_ptr(), std::ptr::null_mut()) };
+    if rc != 0 { return Err(err(ctx.raw, rc)); }
+    Ok((0..n).map(|i| g1_from(&out[12 * i..12 * i + 12], inf[i])).collect())
+}
+pub fn deserialize_g2(ctx: &Context, bytes: &[u8], compressed: bool, validate: bool) -> Result<Vec<G2Affine>, String> {
+    let per = if compressed { 96 } else { 192 };
+    if bytes.len() % per != 0 { return Err("InvalidData: truncated input".into()); }
+    let n = bytes.len() / per;
+    let (mut out, mut inf) = (vec![0u64; 24 * n], vec![0u8; n]);
+    let rc = unsafe { g16_g2_deserialize(ctx.raw, bytes.as_ptr(), n, compressed as c_int, validate as c_int, out.as_mut_ptr(), inf.as_mut_ptr(), std::ptr::null_mut()) };
+    if rc != 0 { return Err(err(ctx.raw, rc)); }
+    Ok((0..n).map(|i| g2_from(&out[24 * i..24 * i + 24], inf[i])).collect())
 }
 
 /// Fixed (r, s) through the unchanged `Prover::prove(pk, witness, rng)` API: `Fr::rand` takes four
