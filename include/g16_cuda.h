@@ -57,8 +57,8 @@ int g16_ctx_synchronize(g16_ctx *ctx);
 /* tuning: window bits for the next MSMs (0 = choose from n) */
 int g16_ctx_set_window_bits(g16_ctx *ctx, unsigned c);
 /* tuning: bucket sums as trees of affine additions with block-shared inversions (6 instead of 10 field
- * multiplications per addition) for `rounds` pairwise rounds before the XYZZ tail; 0 = XYZZ walk only,
- * -1 = choose from the size of the call (default).  Process-wide.  Results are unchanged. */
+ * multiplications per addition) for `rounds` pairwise rounds before the XYZZ tail; 0 or -1 = XYZZ walk only (the
+ * default: measured faster on B200).  Process-wide.  Results are unchanged. */
 int g16_ctx_set_affine_rounds(g16_ctx *ctx, int rounds);
 int g16_device_count(void);
 const char *g16_version(void);

@@ -200,24 +200,22 @@ inline unsigned choose_precompute_c(size_t n, size_t point_bytes, size_t budget)
     return best_c;
 }
 
-// Affine bucket accumulation (affine_acc.cuh): number of pairwise rounds before the XYZZ tail.  -1 = choose from
-// the size of the call: the shared inversions cost latency, not throughput, so the tree pays once there are
-// enough blocks to hide it; small calls keep the XYZZ walk.  Process-wide tuning knob (g16_ctx_set_affine_rounds,
-// or G16_AFFINE_ROUNDS in the environment for experiments).
+// Affine bucket accumulation (affine_acc.cuh): number of pairwise rounds before the XYZZ tail.  Default 0 = the
+// XYZZ walk.  MEASURED (B200, 2^24, c = 22, profiles/README.md runs 13-14): the tree retires ~28 % fewer integer
+// multiplies and its later rounds run at 0.21 ms per million additions against 0.35 for the XYZZ walk, but round 0
+// has to gather every base point twice (denominators, then the additions) from a 19 GB table at 128-byte DRAM
+// granularity -- 80 GB of traffic, 37 ms for half of the additions -- so the whole accumulation takes 78.7 ms
+// instead of 72.7.  Kept, bit-exact and tested, as an opt-in (g16_ctx_set_affine_rounds / G16_AFFINE_ROUNDS).
 inline int &affine_rounds_setting() {
     static int v = getenv("G16_AFFINE_ROUNDS") ? atoi(getenv("G16_AFFINE_ROUNDS")) : -1;
     return v;
 }
 constexpr int AFF_MAX_ROUNDS_API = 8;
-constexpr size_t AFFINE_MIN_ENTRIES = (size_t)1 << 24;
-constexpr size_t AFFINE_MAX_ENTRIES = (size_t)1 << 28;   // scratch: ~96 B per entry
-constexpr uint32_t AFFINE_DEFAULT_ROUNDS = 3;
 inline uint32_t affine_rounds_for(size_t entries, size_t buckets) {
     int v = affine_rounds_setting();
-    if (v >= 0) return (uint32_t)std::min<int>(v, 8);
-    if (entries < AFFINE_MIN_ENTRIES || entries > AFFINE_MAX_ENTRIES) return 0;
-    if (entries < 8 * buckets) return 0;   // nearly empty buckets: nothing to pair
-    return AFFINE_DEFAULT_ROUNDS;
+    if (v <= 0) return 0;
+    (void)entries; (void)buckets;
+    return (uint32_t)std::min<int>(v, AFF_MAX_ROUNDS_API);
 }
 
 constexpr uint32_t REDUCE_LOG_L = 5;
