@@ -82,6 +82,13 @@ struct Device {
 };
 
 inline void set_device(int id);
+inline void set_device_nothrow(int id) {
+#ifndef G16_EMU
+    cudaSetDevice(id);
+#else
+    (void)id;
+#endif
+}
 inline Device &lane_of(Device &dv, int k) {
     if (k == 0) return dv;
     while ((int)dv.extra.size() < k) {
@@ -134,7 +141,8 @@ struct Bases {
     ~Bases() {
         for (auto &s : shards)
         {
-            if ((s.owned && s.pts) || s.table) set_device(ctx->devs[s.dev].id);
+            // destructors must not throw: select the device without the checking wrapper
+            if ((s.owned && s.pts) || s.table) set_device_nothrow(ctx->devs[s.dev].id);
             if (s.owned && s.pts) dev_free(s.pts);
             if (s.table) dev_free(s.table);
         }

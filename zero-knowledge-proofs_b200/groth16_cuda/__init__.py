@@ -16,6 +16,7 @@ CUDA library is present and a device is visible.
 from __future__ import annotations
 
 import ctypes
+import weakref
 import os
 from typing import Optional, Sequence, Tuple
 
@@ -158,6 +159,7 @@ class Bases:
 
     def __init__(self, ctx: "Context", handle: int, group: int, keepalive=None):
         self.ctx, self.handle, self.group, self._keep = ctx, handle, group, keepalive
+        ctx._children.add(self)
 
     def __len__(self):
         return int(self.ctx.lib.g16_bases_len(self.handle))
@@ -184,6 +186,7 @@ class Bases:
 class ProvingKeyDevice:
     def __init__(self, ctx: "Context", handle: int):
         self.ctx, self.handle = ctx, handle
+        ctx._children.add(self)
 
     def free(self):
         if self.handle:
@@ -203,6 +206,7 @@ class R1CSDevice:
 
     def __init__(self, ctx: "Context", handle: int, num_constraints: int, num_variables: int):
         self.ctx, self.handle = ctx, handle
+        ctx._children.add(self)
         self.num_constraints, self.num_variables = num_constraints, num_variables
 
     @property
@@ -224,6 +228,7 @@ class R1CSDevice:
 class Context:
     def __init__(self, devices: Optional[Sequence[int]] = None, lib_path: Optional[str] = None):
         self.lib = load_library(lib_path)
+        self._children = weakref.WeakSet()   # handles that point into this context: freed before it is destroyed
         h = ctypes.c_void_p()
         if devices:
             arr = (ctypes.c_int * len(devices))(*devices)
@@ -241,6 +246,8 @@ class Context:
 
     def close(self):
         if getattr(self, "handle", None):
+            for child in list(self._children):
+                child.free()
             self.lib.g16_ctx_destroy(self.handle)
             self.handle = None
 

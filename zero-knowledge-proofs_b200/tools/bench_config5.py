@@ -145,6 +145,7 @@ def main():
                                       "what": "proof recomputed in the exponent with exact big integers (O(n)), compressed bytes compared"}
             assert exp == line["proof_compressed"], "proof differs from the exponent computation"
         print(json.dumps(line), flush=True)
+    dev_pk.free()
     ctx.close()
 
 
