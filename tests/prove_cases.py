@@ -67,3 +67,31 @@ def check_config1(ctx, golden=None):
         if golden is not None:
             assert golden[name] == out[name], name
     return out
+
+
+def check_random_key(ctx, ctx_single, oracle, gens, n, seed, num_public=2):
+    """Random ProvingKey-shaped arrays (k_i * G) of n variables: the proof of `ctx` (any sharding) equals the proof of
+    the one-device schedule of `ctx_single`, including arrays shorter than the assignment and H of a different length."""
+    import helpers
+    pk = {"num_public": num_public}
+    for i, name in enumerate(("a_g1", "b_g1", "ic_g1", "h_g1")):
+        cnt = {"ic_g1": n - num_public - 1, "h_g1": n + 3}.get(name, n)
+        pk[name], pk[name + "_inf"] = helpers.make_points(oracle, gens, "g1", 0x9e00 + 16 * seed + i, cnt)
+    pk["b_g2"], pk["b_g2_inf"] = helpers.make_points(oracle, gens, "g2", 0x9e80 + seed, n)
+    s1, _ = helpers.make_points(oracle, gens, "g1", 0x9f00 + seed, 3)
+    s2, _ = helpers.make_points(oracle, gens, "g2", 0x9f80 + seed, 2)
+    pk.update(alpha_g1=s1[0], beta_g1=s1[1], delta_g1=s1[2], beta_g2=s2[0], delta_g2=s2[1])
+    w = oracle.gen_scalars(0xa000 + seed, n)
+    w[0] = np.array(bls.fr_to_mont(1), dtype=np.uint64)
+    w[3] = 0                                            # a zero scalar (the reference filters these out)
+    h = oracle.gen_scalars(0xa100 + seed, n - 1)
+    r, s = oracle.gen_scalars(0xa200 + seed, 2)
+    proofs = []
+    for c in (ctx, ctx_single):
+        dev_pk = c.pk_upload(pk)
+        proofs.append(c.prove(dev_pk, w, h, r, s))
+        proofs.append(c.prove(dev_pk, w, None, r, s))  # no H term
+        dev_pk.free()
+    for got, exp in ((proofs[0], proofs[2]), (proofs[1], proofs[3])):
+        for (gx, gi), (ex, ei) in zip(got, exp):
+            assert gi == ei and (gx == ex).all()

@@ -78,8 +78,26 @@ def test_emu_affine_bucket_accumulation(emu_ctx, oracle, gens):
 def test_emu_wire_format(emu_ctx):
     import wire_cases as wc
     wc.check_known_answers(emu_ctx)
+    wc.check_golden(emu_ctx)
     wc.check_roundtrip(emu_ctx, "g1")
     wc.check_roundtrip(emu_ctx, "g2", ks=wc.KS[:6])
     wc.check_rejects(emu_ctx, "g1")
     wc.check_rejects(emu_ctx, "g2")
     wc.check_proof(emu_ctx)
+
+
+def test_emu_prove_multi_device_schedule(emu_ctx, oracle, gens):
+    """g16_prove on a multi-device context (index-range shards of every ProvingKey array, per-device slices of the
+    assignment, partial sums folded on device 0): config-1 proofs, and a random key against the one-device schedule."""
+    import json
+    import os
+    import groth16_cuda
+    import prove_cases
+    golden = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "config1_proofs.json")))
+    for devs in ([0, 1], [0, 1, 2, 3, 4]):
+        ctx = groth16_cuda.Context(devices=devs, lib_path=emu_ctx.lib._name)
+        try:
+            prove_cases.check_config1(ctx, golden)
+            prove_cases.check_random_key(ctx, emu_ctx, oracle, gens, n=23, seed=len(devs))
+        finally:
+            ctx.close()

@@ -188,6 +188,7 @@ def test_wire_format(gpu_ctx, oracle, gens):
     """ark CanonicalSerialize / CanonicalDeserialize of G1Affine, G2Affine and Proof on the device."""
     import wire_cases as wc
     wc.check_known_answers(gpu_ctx)
+    wc.check_golden(gpu_ctx)
     wc.check_roundtrip(gpu_ctx, "g1")
     wc.check_roundtrip(gpu_ctx, "g2")
     wc.check_rejects(gpu_ctx, "g1")

@@ -46,3 +46,17 @@ def test_r1cs_setup_and_prove(gpu_ctx):
 def test_r1cs_large_polynomial_identity(gpu_ctx, oracle):
     import r1cs_cases as rc
     rc.check_large_properties(gpu_ctx, oracle, log_m=12)
+
+
+def test_prove_multi_device_random_key(gpu_ctx, oracle, gens):
+    """Device-chained prove schedule over index-range shards (all GPUs of the box, or two shards on one GPU) against
+    the one-device schedule on a random ProvingKey: lengths that do not divide evenly, arrays of different lengths,
+    zero scalars, with and without H."""
+    import groth16_cuda
+    ndev = gpu_ctx.lib.g16_device_count()
+    for devs in ([0, 0], list(range(min(ndev, 8))) if ndev > 1 else [0, 0, 0]):
+        ctx = groth16_cuda.Context(devices=devs)
+        try:
+            prove_cases.check_random_key(ctx, gpu_ctx, oracle, gens, n=3001, seed=len(devs))
+        finally:
+            ctx.close()

@@ -99,3 +99,44 @@ def test_c_adversarial_vs_naive(oracle, gens):
         a, ai = f(pts, inf, sc)
         b, bi = naive(pts, inf, sc)
         assert ai == bi and (a == b).all()
+
+
+def test_wire_format_oracle(bls):
+    """oracle/bls12_381.py encoder / decoder against the committed fixture and the public generator encodings."""
+    fx = helpers.load_json("wire_cases.json")
+    kat = helpers.load_json("kat.json")
+    assert fx["g1"][1]["compressed"] == kat["g1_gen_compressed"] and fx["g2"][1]["compressed"] == kat["g2_gen_compressed"]
+    for group, from_mont, enc_c, enc_u in (("g1", bls.g1_from_mont, bls.g1_compress, bls.g1_uncompressed),
+                                           ("g2", bls.g2_from_mont, bls.g2_compress, bls.g2_uncompressed)):
+        for c in fx[group]:
+            p = from_mont([int(v, 16) for v in c["limbs"]], c["inf"])
+            assert enc_c(p).hex() == c["compressed"] and enc_u(p).hex() == c["uncompressed"]
+            assert bls.point_deserialize(group, bytes.fromhex(c["compressed"]), True) == p
+            assert bls.point_deserialize(group, bytes.fromhex(c["uncompressed"]), False) == p
+    # rejections: wrong compression flag, non-canonical x, x without a point, a curve point outside the subgroup
+    g = bytes.fromhex(kat["g1_gen_compressed"])
+    with pytest.raises(bls.WireError, match="UnexpectedFlags"):
+        bls.point_deserialize("g1", g, compressed=False)
+    with pytest.raises(bls.WireError, match="InvalidData"):
+        bls.point_deserialize("g1", bytes([0x9f]) + b"\xff" * 47)
+    rejected = accepted_unchecked = 0
+    x = int.from_bytes(bytes([g[0] & 0x1f]) + g[1:], "big")
+    for d in range(1, 12):
+        b = (x + d).to_bytes(48, "big")
+        b = bytes([b[0] | 0x80]) + b[1:]
+        try:
+            bls.point_deserialize("g1", b, validate=True)
+        except bls.WireError:
+            rejected += 1
+        try:
+            p = bls.point_deserialize("g1", b, validate=False)
+            assert bls.G1.on_curve(p)
+            accepted_unchecked += 1
+        except bls.WireError:
+            pass
+    assert rejected == 11 and 0 < accepted_unchecked < 11     # on the curve about half the time, never in the subgroup
+    r2 = bls.fq2_sqrt((3, 5))
+    assert r2 is None or bls.Fq2Ops.sqr(r2) == (3, 5)
+    sq = bls.Fq2Ops.sqr((123456789, 987654321))
+    r2 = bls.fq2_sqrt(sq)
+    assert bls.Fq2Ops.sqr(r2) == sq

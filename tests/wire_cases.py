@@ -128,3 +128,16 @@ def check_proof(ctx):
     assert got == bls.proof_bytes(None, b, None)
     with pytest.raises(groth16_cuda.MSMError):
         ctx.proof_deserialize(got[:100])
+
+
+def check_golden(ctx):
+    """committed fixture (tests/golden/wire_cases.json, made by make_wire_golden.py): bytes <-> ark limbs."""
+    fx = helpers.load_json("wire_cases.json")
+    for group in ("g1", "g2"):
+        xy = helpers.limbs([c["limbs"] for c in fx[group]])
+        inf = np.array([c["inf"] for c in fx[group]], dtype=np.uint8)
+        for mode, compressed in (("compressed", True), ("uncompressed", False)):
+            data = bytes.fromhex("".join(c[mode] for c in fx[group]))
+            assert ctx.serialize_points(group, xy, inf, compressed=compressed) == data
+            bxy, binf = ctx.deserialize_points(group, data, compressed=compressed)
+            assert (bxy == xy).all() and (binf == inf).all()

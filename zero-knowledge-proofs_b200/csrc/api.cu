@@ -473,6 +473,133 @@ void prove_single_device(Context *c, const g16_pk *pk, const uint64_t *w, size_t
     if (b_inf) *b_inf = (uint8_t)rb[48];
     if (c_inf) *c_inf = (uint8_t)rc[24];
 }
+
+// The same schedule on a multi-device context: every resident array is sharded by index range, so device k runs the
+// five MSMs over ITS slices on five lanes; its slice of the assignment (and of the H coefficients) is copied once and
+// shared by the four MSMs that read it -- no host-side concatenation, the (1, r) / (1, s) prefixes are spliced in on
+// the device that owns the head of an array.  The 5 x G partial sums travel to device 0, which folds them, adds the
+// ad-hoc terms of pi_C and returns the proof; the host waits once.
+void prove_multi_device(Context *c, const g16_pk *pk, const uint64_t *w, size_t num_vars, const uint64_t *h, size_t num_h,
+                        const uint64_t *r, const uint64_t *s, uint64_t *a_xy, uint8_t *a_inf, uint64_t *b_xy, uint8_t *b_inf,
+                        uint64_t *c_xy, uint8_t *c_inf) {
+    constexpr size_t PW1 = 48, AW1 = 25, PW2 = 96, AW2 = 49;
+    const size_t G = c->devs.size();
+    const unsigned co = c->c_override;
+    std::vector<uint64_t> hs(4 * 16);
+    auto put = [&](size_t slot, const uint64_t *x) { memcpy(hs.data() + 4 * slot, x, 32); };
+    put(0, FR_ONE_MONT); put(1, r);              // pi_A prefix   [1, r]
+    put(2, FR_ONE_MONT); put(3, s);              // pi_B prefix   [1, s]
+    put(4, FR_ONE_MONT);                         // pi_B' prefix  [1]
+    put(5, FR_ONE_MONT); put(6, s); put(7, r);   // ad-hoc terms of pi_C: [1 * H, s * pi_A, r * pi_B']
+
+    const size_t first_priv = pk->num_public + 1;
+    struct Job { const Bases *bases; size_t prefix, slot, n_src, src_off; int lane; bool g2, from_h; };
+    const Job jobs[5] = {
+        {pk->a.get(), 2, 0, std::min(num_vars, pk->a_len), 0, 0, false, false},
+        {pk->b2.get(), 2, 2, std::min(num_vars, pk->b2_len), 0, 1, true, false},
+        {pk->h.get(), 0, 0, h ? std::min(num_h, pk->h_len) : 0, 0, 2, false, true},
+        {pk->b1.get(), 1, 4, std::min(num_vars, pk->b1_len), 0, 3, false, false},
+        {pk->ic.get(), 0, 0, num_vars > first_priv ? std::min(num_vars - first_priv, pk->ic_len) : 0, first_priv, 4, false, false},
+    };
+    // device 0, lane 4 collects: partial sums [job][device] (G2 slots for all, simpler indexing)
+    Device &d0 = c->devs[0];
+    set_device(d0.id);
+    Device &LC0 = lane_of(d0, 4);
+    uint32_t *parts = LC0.ws.partials.as<uint32_t>(5 * (G + 1) * PW2 + 4 * AW2 + 3 * 24 + 64);
+    auto part_of = [&](int job, size_t k) { return parts + ((size_t)job * (G + 1) + k) * PW2; };
+
+    for (size_t k = 0; k < G; ++k) {
+        Device &dv = c->devs[k];
+        set_device(dv.id);
+        Device *L[5];
+        for (int i = 0; i < 5; ++i) L[i] = &lane_of(dv, i);
+        // slice of every job on this device, and the range of the assignment they read
+        size_t lo[5], hi[5], wlo = ~(size_t)0, whi = 0;
+        for (int j = 0; j < 5; ++j) {
+            const Job &jb = jobs[j];
+            size_t n_total = jb.prefix + jb.n_src;
+            const BasesShard &sh = jb.bases->shards[k];
+            lo[j] = std::min(sh.begin, n_total); hi[j] = std::min(sh.begin + sh.n, n_total);
+            if (!jb.from_h && hi[j] > std::max(lo[j], jb.prefix)) {
+                wlo = std::min(wlo, std::max(lo[j], jb.prefix) - jb.prefix + jb.src_off);
+                whi = std::max(whi, hi[j] - jb.prefix + jb.src_off);
+            }
+        }
+        if (whi <= wlo) { wlo = 0; whi = 0; }
+        uint32_t *d_w = L[0]->ws.prove_w.as<uint32_t>((whi - wlo) * 8 + 8);
+        copy_h2d(d_w, w + wlo * 4, (whi - wlo) * 32, L[0]->stream);
+        uint32_t *d_small = L[0]->ws.prove_misc.as<uint32_t>(16 * 8 + 64);
+        copy_h2d(d_small, hs.data(), 16 * 32, L[0]->stream);
+        for (int i = 1; i < 5; ++i) stream_wait(L[i]->stream, L[0]->stream);
+        for (int j = 0; j < 5; ++j) {
+            const Job &jb = jobs[j];
+            Device &ln = *L[jb.lane];
+            const BasesShard &sh = jb.bases->shards[k];
+            size_t cnt = hi[j] - lo[j];
+            const size_t PW = jb.g2 ? PW2 : PW1;
+            uint32_t *d_out = ln.ws.out.as<uint32_t>(PW2 + AW2);
+            const uint32_t *d_sc = nullptr;
+            if (cnt) {
+                if (jb.from_h) {
+                    uint32_t *d_h = ln.ws.scalars.as<uint32_t>(cnt * 8 + 8);
+                    copy_h2d(d_h, h + lo[j] * 4, cnt * 32, ln.stream);
+                    d_sc = d_h;
+                } else if (lo[j] >= jb.prefix) {
+                    d_sc = d_w + (lo[j] - jb.prefix + jb.src_off - wlo) * 8;   // a plain slice of the assignment
+                } else {
+                    // head of the array: prefix scalars, then the assignment from its first element
+                    uint32_t *d = ln.ws.scalars.as<uint32_t>(cnt * 8 + 8);
+                    size_t np = std::min(jb.prefix, hi[j]) - lo[j];
+                    copy_d2d(d, d_small + (jb.slot + lo[j]) * 8, np * 32, ln.stream);
+                    copy_d2d(d + np * 8, d_w + (jb.src_off - wlo) * 8, (cnt - np) * 32, ln.stream);
+                    d_sc = d;
+                }
+            }
+            if (jb.g2) msm_run<Fq2>(ln, sh, d_sc, cnt, true, co, d_out, nullptr, lo[j] - std::min(lo[j], sh.begin));
+            else msm_run<Fq>(ln, sh, d_sc, cnt, true, co, d_out, nullptr, lo[j] - std::min(lo[j], sh.begin));
+            copy_peer(part_of(j, k), d_out, PW * 4, ln.stream);
+        }
+    }
+    // device 0: wait for every lane of every device, fold, finish pi_C
+    for (size_t k = 0; k < G; ++k)
+        for (int i = 0; i < 5; ++i) {
+            Device &ln = lane_of(c->devs[k], i);
+            if (&ln != &LC0) stream_wait_xdev(LC0.stream, d0.id, ln.stream, c->devs[k].id);
+        }
+    set_device(d0.id);
+    uint32_t *aff = parts + 5 * (G + 1) * PW2;               // A, B (G2), H, B' affine results, AW2 words apart
+    uint32_t *oa = aff, *ob = aff + AW2, *oh = aff + 2 * AW2, *ob1 = aff + 3 * AW2;
+    uint32_t *d_adhoc_pts = aff + 4 * AW2;                   // 3 packed G1 points
+    auto fold_g1 = [&](int job, uint32_t *out_aff) {
+        // G1 partials sit PW2 words apart: compact them in place before the fold (slot 0 stays)
+        for (size_t k = 1; k < G; ++k) copy_d2d(part_of(job, 0) + k * PW1, part_of(job, k), PW1 * 4, LC0.stream);
+        k_partial_combine<Fq>(LC0.stream, part_of(job, 0), (uint32_t)G, nullptr, out_aff);
+    };
+    fold_g1(0, oa);
+    k_partial_combine<Fq2>(LC0.stream, part_of(1, 0), (uint32_t)G, nullptr, ob);
+    fold_g1(2, oh);
+    fold_g1(3, ob1);
+    copy_d2d(d_adhoc_pts, oh, 96, LC0.stream);
+    copy_d2d(d_adhoc_pts + 24, oa, 96, LC0.stream);
+    copy_d2d(d_adhoc_pts + 48, ob1, 96, LC0.stream);
+    for (size_t k = 1; k < G; ++k) copy_d2d(part_of(4, 0) + k * PW1, part_of(4, k), PW1 * 4, LC0.stream);
+    BasesShard adhoc;
+    adhoc.dev = 0; adhoc.pts = d_adhoc_pts; adhoc.n = 3; adhoc.owned = false;
+    const uint32_t *d_small0 = (const uint32_t *)lane_of(d0, 0).ws.prove_misc.p;
+    msm_run<Fq>(LC0, adhoc, d_small0 + 5 * 8, 3, true, 0, part_of(4, 0) + G * PW1, nullptr);
+    uint32_t *d_c_aff = d_adhoc_pts + 3 * 24;
+    k_partial_combine<Fq>(LC0.stream, part_of(4, 0), (uint32_t)G + 1, nullptr, d_c_aff);
+
+    uint32_t ra[AW1], rb[AW2], rc[AW1];
+    copy_d2h(ra, oa, AW1 * 4, LC0.stream);
+    copy_d2h(rb, ob, AW2 * 4, LC0.stream);
+    copy_d2h(rc, d_c_aff, AW1 * 4, LC0.stream);
+    stream_sync(LC0.stream);
+    memcpy(a_xy, ra, 96); memcpy(b_xy, rb, 192); memcpy(c_xy, rc, 96);
+    if (a_inf) *a_inf = (uint8_t)ra[24];
+    if (b_inf) *b_inf = (uint8_t)rb[48];
+    if (c_inf) *c_inf = (uint8_t)rc[24];
+}
 }  // extern "C++"
 
 // The MSM schedule of Prover::prove (crates/groth16-core/src/lib.rs:164-271).  The reference
@@ -493,64 +620,7 @@ int g16_prove(g16_ctx *ctx, const g16_pk *pk, const uint64_t *assignment_fr, siz
             prove_single_device(c, pk, assignment_fr, num_vars, h_coeffs, num_h, r, s, a_xy, a_inf, b_xy, b_inf, c_xy, c_inf, nullptr);
             return;
         }
-        auto put = [](std::vector<uint64_t> &v, const uint64_t *x) { v.insert(v.end(), x, x + 4); };
-        uint8_t inf_a = 0, inf_b = 0, inf_b1 = 0, inf_h = 1, inf_c = 0;
-
-        // The four independent MSMs are launched on four lanes (streams) before any of them is awaited,
-        // so the latency-bound tails of one overlap the bucket accumulation of the others.
-        // pi_A = alpha + sum w_i a_i + r delta                                        (lib.rs:164-179)
-        size_t na = std::min(num_vars, pk->a_len);
-        std::vector<uint64_t> sc_a, sc_b, sc_b1;
-        sc_a.reserve((na + 2) * 4);
-        put(sc_a, FR_ONE_MONT); put(sc_a, r);
-        sc_a.insert(sc_a.end(), assignment_fr, assignment_fr + na * 4);
-        msm_launch<Fq>(c, pk->a.get(), sc_a.data(), na + 2, 0);
-
-        // pi_B = beta + sum w_i b_i + s delta  (G2)                                   (lib.rs:182-197)
-        size_t nb2 = std::min(num_vars, pk->b2_len);
-        put(sc_b, FR_ONE_MONT); put(sc_b, s);
-        sc_b.insert(sc_b.end(), assignment_fr, assignment_fr + nb2 * 4);
-        msm_launch<Fq2>(c, pk->b2.get(), sc_b.data(), nb2 + 2, 1);
-
-        // [H(s)]_1                                                                      (lib.rs:211-221)
-        uint64_t h_xy[12] = {0};
-        size_t nh = h_coeffs ? std::min(num_h, pk->h_len) : 0;
-        if (nh) msm_launch<Fq>(c, pk->h.get(), h_coeffs, nh, 2);
-
-        // pi_B' = beta_1 + sum w_i b_g1[i]                                              (lib.rs:246-255)
-        size_t nb1 = std::min(num_vars, pk->b1_len);
-        uint64_t b1_xy[12];
-        put(sc_b1, FR_ONE_MONT);
-        sc_b1.insert(sc_b1.end(), assignment_fr, assignment_fr + nb1 * 4);
-        msm_launch<Fq>(c, pk->b1.get(), sc_b1.data(), nb1 + 1, 3);
-
-        // main part of pi_C (private-input terms) on lane 0 behind pi_A                 (lib.rs:224-233)
-        size_t first_priv = pk->num_public + 1;
-        size_t nic = num_vars > first_priv ? std::min(num_vars - first_priv, pk->ic_len) : 0;
-        uint64_t cm_xy[12] = {0};
-        uint8_t inf_cm = 1;
-
-        msm_finish<Fq>(c, pk->a.get(), 0, a_xy, &inf_a);
-        if (nic) msm_launch<Fq>(c, pk->ic.get(), assignment_fr + first_priv * 4, nic, 0);
-        if (nh) msm_finish<Fq>(c, pk->h.get(), 2, h_xy, &inf_h);
-        msm_finish<Fq>(c, pk->b1.get(), 3, b1_xy, &inf_b1);
-        if (nic) msm_finish<Fq>(c, pk->ic.get(), 0, cm_xy, &inf_cm);
-        std::vector<uint64_t> sc;
-
-        // pi_C = sum_{private} w_i ic_i + H + s pi_A + r pi_B'                          (lib.rs:224-265)
-        uint64_t adhoc_xy[4 * 12];
-        uint8_t adhoc_inf[4] = {inf_cm, inf_h, inf_a, inf_b1};
-        memcpy(adhoc_xy, cm_xy, 96); memcpy(adhoc_xy + 12, h_xy, 96); memcpy(adhoc_xy + 24, a_xy, 96); memcpy(adhoc_xy + 36, b1_xy, 96);
-        sc.clear();
-        put(sc, FR_ONE_MONT); put(sc, FR_ONE_MONT); put(sc, s); put(sc, r);
-        {
-            std::unique_ptr<Bases> adhoc = bases_upload<Fq>(c, adhoc_xy, adhoc_inf, 4);
-            msm_host<Fq>(c, adhoc.get(), sc.data(), 4, c_xy, &inf_c);
-        }
-        msm_finish<Fq2>(c, pk->b2.get(), 1, b_xy, &inf_b);   // the G2 MSM ran beside everything above
-        if (a_inf) *a_inf = inf_a;
-        if (b_inf) *b_inf = inf_b;
-        if (c_inf) *c_inf = inf_c;
+        prove_multi_device(c, pk, assignment_fr, num_vars, h_coeffs, num_h, r, s, a_xy, a_inf, b_xy, b_inf, c_xy, c_inf);
     });
 }
 

@@ -403,25 +403,35 @@ std::unique_ptr<Bases> bases_upload(Context *ctx, const uint64_t *xy, const uint
 template <class F>
 unsigned bases_precompute(Context *ctx, Bases *bases, unsigned c, size_t budget_bytes) {
     unsigned used = 0;
-    for (auto &sh : bases->shards) {
-        if (sh.n == 0) continue;
-        Device &dv = ctx->devs[sh.dev];
-        set_device(dv.id);
-        size_t point_bytes = 2 * FieldWords<F>::N * 4;
-        unsigned cc = c ? c : choose_precompute_c(sh.n, point_bytes, budget_bytes);
-        if (!c && cc == 0) continue;   // nothing fits the budget: this shard stays plain
-        if (cc < 8 || cc > 24) throw Error{G16_ERR_INVALID, "precompute window bits must be in [8, 24]"};
-        uint32_t nwin = (256 + cc - 1) / cc;
-        if ((double)nwin * (double)sh.n >= 2147483648.0) throw Error{G16_ERR_INVALID, "precomputed table exceeds 2^31 points"};
-        if (sh.table) { dev_free(sh.table); sh.table = nullptr; sh.pre_c = 0; }
-        uint32_t *table = (uint32_t *)dev_alloc((size_t)nwin * sh.n * point_bytes);
-        try {
+    struct Pending { BasesShard *sh; uint32_t *table; unsigned cc; };
+    std::vector<Pending> pending;
+    auto drop = [&] {
+        for (auto &p : pending) { set_device_nothrow(ctx->devs[p.sh->dev].id); dev_free(p.table); }
+    };
+    try {
+        // launch on every device first (the shards are independent), then wait for all of them
+        for (auto &sh : bases->shards) {
+            if (sh.n == 0) continue;
+            Device &dv = ctx->devs[sh.dev];
+            set_device(dv.id);
+            size_t point_bytes = 2 * FieldWords<F>::N * 4;
+            unsigned cc = c ? c : choose_precompute_c(sh.n, point_bytes, budget_bytes);
+            if (!c && cc == 0) continue;   // nothing fits the budget: this shard stays plain
+            if (cc < 8 || cc > 24) throw Error{G16_ERR_INVALID, "precompute window bits must be in [8, 24]"};
+            uint32_t nwin = (256 + cc - 1) / cc;
+            if ((double)nwin * (double)sh.n >= 2147483648.0) throw Error{G16_ERR_INVALID, "precomputed table exceeds 2^31 points"};
+            if (sh.table) { dev_free(sh.table); sh.table = nullptr; sh.pre_c = 0; }
+            uint32_t *table = (uint32_t *)dev_alloc((size_t)nwin * sh.n * point_bytes);
+            pending.push_back(Pending{&sh, table, cc});
             k_precompute_bases<F>(dv.stream, sh.n, sh.pts, cc, nwin, table);
+        }
+        for (auto &p : pending) {
+            Device &dv = ctx->devs[p.sh->dev];
+            set_device(dv.id);
             stream_sync(dv.stream);
-        } catch (...) { dev_free(table); throw; }
-        sh.table = table; sh.pre_c = cc;
-        used = cc;
-    }
+        }
+    } catch (...) { drop(); throw; }
+    for (auto &p : pending) { p.sh->table = p.table; p.sh->pre_c = p.cc; used = p.cc; }
     return used;
 }
 

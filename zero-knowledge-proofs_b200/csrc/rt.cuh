@@ -111,6 +111,31 @@ inline void stream_wait(stream_t waiter, stream_t producer) {
 #endif
 }
 
+// the same across devices: the event is created and recorded on the producer's device, the wait is queued on the
+// waiter's; the current device is left at the waiter's
+inline void stream_wait_xdev(stream_t waiter, int waiter_dev, stream_t producer, int producer_dev) {
+#ifndef G16_EMU
+    cudaEvent_t ev;
+    G16_CUDA_CHECK(cudaSetDevice(producer_dev));
+    G16_CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    G16_CUDA_CHECK(cudaEventRecord(ev, producer));
+    G16_CUDA_CHECK(cudaSetDevice(waiter_dev));
+    G16_CUDA_CHECK(cudaStreamWaitEvent(waiter, ev, 0));
+    G16_CUDA_CHECK(cudaEventDestroy(ev));
+#else
+    (void)waiter; (void)waiter_dev; (void)producer; (void)producer_dev;
+#endif
+}
+// copy between two devices of one process (unified addressing picks the route), queued on the source's stream
+inline void copy_peer(void *dst, const void *src, size_t bytes, stream_t s) {
+    if (!bytes) return;
+#ifndef G16_EMU
+    G16_CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, s));
+#else
+    (void)s; memmove(dst, src, bytes);
+#endif
+}
+
 // atomic add usable from kernel bodies
 G16_HD uint32_t atomic_add_u32(uint32_t *p, uint32_t v) {
 #if G16_DEVICE_CODE

@@ -348,23 +348,28 @@ class Context:
         self._check(getattr(self.lib, f"g16_{g}_combine_partials_device")(self.handle, dev_partials, k, dev_out_affine))
 
     # ---- fixed base
-    def _fixed(self, g: str, base_xy, scalars):
+    def _fixed(self, g: str, base_xy, scalars, out=None):
         width = G1_WORDS64 if g == "g1" else G2_WORDS64
         base_xy = _u64(base_xy).reshape(width)
         scalars = _u64(scalars, 4)
         n = scalars.shape[0]
-        out = np.zeros((n, width), dtype=np.uint64)
-        inf = np.zeros(n, dtype=np.uint8)
+        if out is None:
+            out, inf = np.zeros((n, width), dtype=np.uint64), np.zeros(n, dtype=np.uint8)
+        else:   # caller-owned result buffers (e.g. pinned host memory), the C ABI's own convention
+            out, inf = out
+            assert out.dtype == np.uint64 and out.shape == (n, width) and out.flags.c_contiguous
+            assert inf.dtype == np.uint8 and inf.shape == (n,)
         self._check(getattr(self.lib, f"g16_{g}_fixed_base_mul")(self.handle, _ptr(base_xy), _ptr(scalars), n,
                                                                 _ptr(out), _ptr(inf)))
         return out, inf
 
-    def fixed_base_mul_g1(self, base_xy, scalars):
-        """[(base * s).into_affine() for s in scalars] (crates/groth16-setup/src/lib.rs:185-241)."""
-        return self._fixed("g1", base_xy, scalars)
+    def fixed_base_mul_g1(self, base_xy, scalars, out=None):
+        """[(base * s).into_affine() for s in scalars] (crates/groth16-setup/src/lib.rs:185-241).
+        out = (xy[n, 12] uint64, inf[n] uint8) to receive the result in caller-owned memory."""
+        return self._fixed("g1", base_xy, scalars, out)
 
-    def fixed_base_mul_g2(self, base_xy, scalars):
-        return self._fixed("g2", base_xy, scalars)
+    def fixed_base_mul_g2(self, base_xy, scalars, out=None):
+        return self._fixed("g2", base_xy, scalars, out)
 
     def fixed_base_mul_device(self, g: str, base_xy, dev_scalars: int, n: int, dev_out: int):
         width = G1_WORDS64 if g == "g1" else G2_WORDS64

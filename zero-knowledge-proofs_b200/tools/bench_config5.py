@@ -42,6 +42,7 @@ def main():
     ap.add_argument("--sample", type=int, default=1 << 10)
     ap.add_argument("--check-exponent", action="store_true")
     ap.add_argument("--no-precompute", action="store_true")
+    ap.add_argument("--pageable", action="store_true", help="plain numpy host buffers instead of pinned host memory")
     ap.add_argument("--lib", default=None, help="library path (tests only: the host-emulation build)")
     args = ap.parse_args()
     import ctypes
@@ -55,19 +56,31 @@ def main():
     g2 = np.array(bls.g2_to_mont(bls.G2_GEN)[0], dtype=np.uint64)
     th = oracle.max_threads()
     R = bls.R
+    if args.pageable or args.lib:
+        pin = lambda a: a                                    # noqa: E731
+        host_kind = "pageable"
+    else:
+        import torch                                         # pinned host memory only (torch owns the allocator)
+
+        def pin(a):
+            t = torch.from_numpy(np.ascontiguousarray(a).view(np.int64) if a.dtype == np.uint64 else np.ascontiguousarray(a))
+            return t.pin_memory().numpy().view(a.dtype)
+        host_kind = "pinned"
 
     # ---- setup: fixed-base multiplications, host scalars -> host points ---------------------------------
     names = ("a_g1", "b_g1", "ic_g1", "h_g1", "vk_ic_g1")
     for dist, bits in (("ref_faithful_u64", 64), ("full_width", 255)):
-        ks = {nm: oracle.gen_scalars(0xc5e700 + 16 * i + bits, n, bits) for i, nm in enumerate(names + ("b_g2",))}
+        ks = {nm: pin(oracle.gen_scalars(0xc5e700 + 16 * i + bits, n, bits)) for i, nm in enumerate(names + ("b_g2",))}
+        outs = {nm: (pin(np.zeros((n, 24 if nm == "b_g2" else 12), dtype=np.uint64)), pin(np.zeros(n, dtype=np.uint8)))
+                for nm in names + ("b_g2",)}
         ctx.fixed_base_mul_g1(g1, ks["a_g1"][:4096])          # warm-up: tables, workspaces
         ctx.fixed_base_mul_g2(g2, ks["b_g2"][:4096])
         t0 = time.perf_counter()
         pts = {}
         for nm in names:
-            pts[nm] = ctx.fixed_base_mul_g1(g1, ks[nm])
+            pts[nm] = ctx.fixed_base_mul_g1(g1, ks[nm], out=outs[nm])
         t_g1 = time.perf_counter() - t0
-        pts["b_g2"] = ctx.fixed_base_mul_g2(g2, ks["b_g2"])
+        pts["b_g2"] = ctx.fixed_base_mul_g2(g2, ks["b_g2"], out=outs["b_g2"])
         t_all = time.perf_counter() - t0
         m = min(n, args.sample)
         ok = True
@@ -83,7 +96,8 @@ def main():
         cpu_rate = (6 * (m + 8)) / cpu_s
         print(json.dumps({"metric": "groth16_setup_group_ms", "config": f"5 x 2^{args.log_n} G1 + 2^{args.log_n} G2 fixed-base, {dist}",
                           "n_gpus": args.gpus, "ms": t_all * 1e3, "g1_ms": t_g1 * 1e3, "g2_ms": (t_all - t_g1) * 1e3,
-                          "points_per_s": 6 * n / t_all, "through": "C ABI, host scalars in, host points out (pageable)",
+                          "points_per_s": 6 * n / t_all, "through": f"C ABI, host scalars in, host points out ({host_kind} host memory)",
+                          "h2d_bytes": 6 * n * 32, "d2h_bytes": n * (5 * 97 + 193),
                           "cpu_points_per_s_mixed": cpu_rate, "cpu_threads": th, "bit_exact_sample": ok,
                           "sample": f"first {m} + last 8 of each array"}), flush=True)
         assert ok, "setup sample differs from the CPU oracle"
@@ -112,7 +126,8 @@ def main():
     for dist, bits in (("ref_faithful_u64", 64), ("full_width", 255)):
         w = oracle.gen_scalars(0x1000 + bits, n, bits)
         w[0] = one
-        h = oracle.gen_scalars(0x2000 + bits, n - 1, bits)
+        w = pin(w)
+        h = pin(oracle.gen_scalars(0x2000 + bits, n - 1, bits))
         for _ in range(2):
             proof = ctx.prove(dev_pk, w, h, r, s)
         t0 = time.perf_counter()
@@ -121,7 +136,8 @@ def main():
         ms = (time.perf_counter() - t0) / args.steps * 1e3
         line = {"metric": "groth16_prove_ms", "config": f"ProvingKey from the setup above, N = n = 2^{args.log_n}, 1 public input, {dist}",
                 "n_gpus": args.gpus, "gpu_ms": ms, "msms": "4 x G1 + 1 x G2 (+ ad-hoc terms)", "pk_upload_s": upload_s,
-                "pk_precompute_s": pre_s, "through": "g16_prove: host assignment + H coefficients in, proof out",
+                "pk_precompute_s": pre_s, "through": f"g16_prove: host assignment + H coefficients in ({host_kind} host memory), proof out",
+                "h2d_bytes_per_prove": (2 * n - 1) * 32, "d2h_bytes_per_prove": 51 * 4,
                 "proof_compressed": ctx.proof_serialize(*proof).hex() if args.gpus == 1 else None}
         if args.gpus > 1:
             # the wire-format entry points are single-device: serialise on a one-GPU context
