@@ -351,6 +351,12 @@ def main():
     if roof["achieved"] and roof["peak"]:
         roof["frac"] = roof["achieved"] / roof["peak"]
         roof["whole_step_frac"] = value / world * FQ_MUL_PER_PAIR * IMAD_PER_FQ_MUL / imad_peak_per_s
+    if acc_ms and (peak or {}).get("fq_mul_per_s"):
+        # what the kernel actually executes: one XYZZ mixed addition (8M + 2S) per non-zero digit, against the
+        # measured throughput of the engine's own Fq multiplication (lib/imad_peak)
+        ex = float(n_loc) * float(plan[1]) * 10.0 / (acc_ms * 1e-3)
+        roof["executed"] = {"fq_mul_per_pair": int(plan[1]) * 10, "fq_mul_per_s": ex,
+                            "fq_mul_peak_per_s": peak["fq_mul_per_s"], "frac_of_fq_mul_peak": ex / peak["fq_mul_per_s"]}
     if acc_ms:
         pt_bytes = float(n_loc) * float(plan[1]) * 96.0
         roof["point_stream_hbm"] = {"achieved_GBps": pt_bytes / (acc_ms * 1e-3) / 1e9,

@@ -121,7 +121,7 @@ def _dot_mod_r(a_mont, b_mont, oracle):
     return acc % bls.R
 
 
-@pytest.mark.parametrize("log_n", [20])
+@pytest.mark.parametrize("log_n", [20, 22])
 def test_large_msm_by_discrete_log(gpu_ctx, oracle, gens, log_n):
     """Size-independent exact check at sizes the CPU oracle cannot reach in seconds: with bases
     P_i = k_i G (built on the GPU by the fixed-base kernel), sum s_i P_i must equal (sum s_i k_i mod r) G,
@@ -161,6 +161,12 @@ def test_large_msm_by_discrete_log(gpu_ctx, oracle, gens, log_n):
     e2 = _dot_mod_r(s2, k, oracle)
     exp2, _ = oracle.g1_fixed_base_mul(gens[0], np.array([bls.fr_to_mont(e2)], dtype=np.uint64))
     assert (host2[:24].view(np.uint64) == exp2[0]).all()
+    # the same sum over precomputed multiples (one shared bucket set; at 2^22 the entry array exceeds L2 and goes
+    # through the two-pass partitioned scatter, as do the per-window bucket sets above)
+    bases.precompute(0)
+    gpu_ctx.msm_device("g1", bases, d_s2.data_ptr(), n, out.data_ptr(), 0)
+    torch.cuda.synchronize()
+    assert (out.cpu().numpy().view(np.uint32)[:24].view(np.uint64) == exp2[0]).all()
     bases.free()
 
 

@@ -13,13 +13,13 @@ enum Group { GROUP_G1 = 1, GROUP_G2 = 2 };
 template <class F> struct GroupOf { static constexpr int id = FieldWords<F>::group; };
 
 struct Workspace {
-    DevBuf scalars, counts, codes, ranks, bins, items, item_start, chunk_out, cursor, entries, buckets, affine, red[6], scan_tmp, out, partials, staging;
+    DevBuf scalars, counts, codes, ranks, bins, items, item_start, chunk_out, cursor, entries, buckets, affine, scatter_stage, red[6], scan_tmp, out, partials, staging;
     DevBuf prove_w, prove_misc, ntt_abc, ntt_tw, ntt_consts, ntt_out;
     uint32_t ntt_log_n = 0xffffffffu;   // size the cached twiddles / constants were built for (none yet)
     DevBuf fb_base, fb_powers, fb_table[3], fb_out, fb_flags;
     std::vector<uint32_t> fb_table_key[3];  // base limbs the cached table was built for
     void release() {
-        scalars.release(); counts.release(); codes.release(); ranks.release(); bins.release(); items.release(); item_start.release(); chunk_out.release(); cursor.release(); entries.release(); buckets.release(); affine.release();
+        scalars.release(); counts.release(); codes.release(); ranks.release(); bins.release(); items.release(); item_start.release(); chunk_out.release(); cursor.release(); entries.release(); buckets.release(); affine.release(); scatter_stage.release();
         for (auto &r : red) r.release();
         scan_tmp.release(); out.release(); partials.release(); staging.release();
         prove_w.release(); prove_misc.release(); ntt_abc.release(); ntt_tw.release(); ntt_consts.release(); ntt_out.release(); ntt_log_n = 0xffffffffu; fb_base.release(); fb_powers.release(); fb_out.release(); fb_flags.release();
@@ -226,6 +226,7 @@ inline uint32_t affine_rounds_for(size_t entries, size_t buckets) {
     return (uint32_t)std::min<int>(v, AFF_MAX_ROUNDS_API);
 }
 
+constexpr size_t SCATTER_TWO_PASS_BYTES = (size_t)96 << 20;   // `entries` larger than this (~L2) are scattered in two passes
 constexpr uint32_t REDUCE_LOG_L = 5;
 constexpr size_t TILE_LEVEL_MAX = 1u << 16;   // levels with at most this many entries run block-cooperatively
 constexpr size_t THREAD_LEVEL_GROUPS = 1u << 16;   // groups a thread level aims to leave behind
@@ -293,6 +294,14 @@ void msm_run(Device &dv, const BasesShard &sh, const uint32_t *d_scalars, size_t
         static const size_t slab_bytes = getenv("G16_SCATTER_SLAB_MB") ? (size_t)atol(getenv("G16_SCATTER_SLAB_MB")) << 20 : (size_t)0;   // off: measured slower (one thread per code per slab)
         size_t slabs = (plan.bwin == 1 && slab_bytes) ? (max_entries * 4 + slab_bytes - 1) / slab_bytes : 1;
         if (slabs > 64) slabs = 64;
+        // entry arrays beyond L2 go through the two-pass partitioned scatter (msm_kernels.cuh); G16_SCATTER_ONE_PASS
+        // keeps the one-pass kernel for comparison
+        static const bool one_pass = getenv("G16_SCATTER_ONE_PASS") != nullptr;
+        if (!one_pass && slabs == 1 && max_entries * 4 > SCATTER_TWO_PASS_BYTES) {
+            uint32_t *staging = ws.scatter_stage.as<uint32_t>(2 * max_entries + 2);
+            uint32_t *part_cursor = ws.cursor.as<uint32_t>((max_entries >> k_scatter_log_part(max_entries)) + 2);
+            k_scatter_partitioned(s, n, codes, ranks, plan, offsets, max_entries, part_cursor, staging, entries);
+        } else
         for (size_t k = 0; k < slabs; ++k) {
             uint32_t b_lo = (uint32_t)((uint64_t)plan.nb * k / slabs), b_hi = (uint32_t)((uint64_t)plan.nb * (k + 1) / slabs);
             k_scatter_ranked(s, n, codes, ranks, plan, offsets, b_lo, b_hi, entries);

@@ -14,6 +14,32 @@ void k_scatter_ranked(stream_t s, size_t n, const uint32_t *codes, const uint32_
                       const uint32_t *offsets, uint32_t b_lo, uint32_t b_hi, uint32_t *entries) {
     launch<ScatterRanked>(n * plan.nwin, s, codes, ranks, plan, n, offsets, b_lo, b_hi, entries);
 }
+// partitions of 2^17 entries (512 KB of `entries`) unless that needs more counters than a block holds
+uint32_t k_scatter_log_part(size_t max_entries) {
+    uint32_t lp = 17;
+    while (((max_entries >> lp) + 1) > SCATTER_MAX_PARTS) ++lp;
+    return lp;
+}
+void k_scatter_partitioned(stream_t s, size_t n, const uint32_t *codes, const uint32_t *ranks, MsmPlan plan,
+                           const uint32_t *offsets, size_t max_entries, uint32_t *part_cursor, uint32_t *staging,
+                           uint32_t *entries) {
+#ifndef G16_EMU
+    uint32_t log_part = k_scatter_log_part(max_entries);
+    uint32_t n_parts = (uint32_t)(max_entries >> log_part) + 1;
+    size_t total = n * plan.nwin;
+    size_t blocks = (total + SCATTER_TILE - 1) / SCATTER_TILE;
+    G16_CUDA_CHECK(cudaMemsetAsync(part_cursor, 0, n_parts * sizeof(uint32_t), s));
+    scatter_partition_kernel<<<(unsigned)blocks, SCATTER_THREADS, n_parts * sizeof(uint32_t), s>>>(
+        codes, ranks, plan, n, offsets, log_part, n_parts, part_cursor, reinterpret_cast<uint2 *>(staging));
+    G16_CUDA_CHECK(cudaGetLastError());
+    note_launch();
+    // the entry count sits behind the last bucket offset
+    launch<ScatterFinal>(max_entries, s, (const uint32_t *)staging, offsets + plan.total, entries);
+#else
+    (void)max_entries; (void)part_cursor; (void)staging;
+    launch<ScatterRanked>(n * plan.nwin, s, codes, ranks, plan, n, offsets, 0u, plan.nb, entries);
+#endif
+}
 void k_scatter_by_window(stream_t s, size_t n, const uint32_t *codes, MsmPlan plan, uint32_t *cursor, uint32_t *entries) {
     launch<ScatterByWindow>(n * plan.nwin, s, codes, plan, n, cursor, entries);
 }
@@ -22,11 +48,25 @@ size_t k_item_bytes() { return sizeof(WorkItem); }
 uint32_t k_item_max() { return ITEM_MAX; }
 uint32_t k_tile_entries() { return (uint32_t)(TILE_K * TILE_ELEMS); }
 void k_item_count(stream_t s, size_t buckets, const uint32_t *offsets, uint32_t item_max, uint32_t *bin_counts) {
+#ifndef G16_EMU
+    if (!buckets) return;
+    item_count_kernel<<<(unsigned)((buckets + 255) / 256), 256, 0, s>>>(buckets, offsets, item_max, bin_counts);
+    G16_CUDA_CHECK(cudaGetLastError());
+    note_launch();
+#else
     launch<ItemCount>(buckets, s, offsets, item_max, bin_counts);
+#endif
 }
 void k_item_scatter(stream_t s, size_t buckets, const uint32_t *offsets, uint32_t item_max, uint32_t *bin_cursor,
                     WorkItem *items, uint32_t *split_list) {
+#ifndef G16_EMU
+    if (!buckets) return;
+    item_scatter_kernel<<<(unsigned)((buckets + 255) / 256), 256, 0, s>>>(buckets, offsets, item_max, bin_cursor, items, split_list);
+    G16_CUDA_CHECK(cudaGetLastError());
+    note_launch();
+#else
     launch<ItemScatter>(buckets, s, offsets, item_max, bin_cursor, items, split_list);
+#endif
 }
 size_t k_scan_tmp_words(size_t n) { return scan_tmp_words(n); }
 void k_exclusive_scan(stream_t s, const uint32_t *in, uint32_t *out, size_t n, uint32_t *tmp) {

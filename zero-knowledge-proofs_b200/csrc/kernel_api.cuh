@@ -32,6 +32,12 @@ void k_digit_decompose(stream_t s, size_t n, const uint32_t *scalars, bool mont,
                         uint32_t *codes, uint32_t *ranks);
 void k_scatter_ranked(stream_t s, size_t n, const uint32_t *codes, const uint32_t *ranks, MsmPlan plan,
                       const uint32_t *offsets, uint32_t b_lo, uint32_t b_hi, uint32_t *entries);
+// two-pass scatter through a staging area of (position, entry) pairs (device build only; see msm_kernels.cuh):
+// staging holds 2 words per entry, part_cursor k_scatter_parts(..) zeroed words
+uint32_t k_scatter_log_part(size_t max_entries);
+void k_scatter_partitioned(stream_t s, size_t n, const uint32_t *codes, const uint32_t *ranks, MsmPlan plan,
+                           const uint32_t *offsets, size_t max_entries, uint32_t *part_cursor, uint32_t *staging,
+                           uint32_t *entries);
 void k_scatter_by_window(stream_t s, size_t n, const uint32_t *codes, MsmPlan plan, uint32_t *cursor, uint32_t *entries);
 // work items (bucket slices ordered by length); see msm_kernels.cuh
 struct WorkItem;

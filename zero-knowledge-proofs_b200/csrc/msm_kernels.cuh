@@ -105,6 +105,72 @@ struct ScatterRanked {
     }
 };
 
+// Two-pass scatter for entry arrays far larger than L2 (shared bucket set at 2^24: 800 MB).  The one-pass kernel
+// above writes 4 bytes at a random position per digit, and DRAM turns each of them into a read-modify-write of a
+// whole line (6.9 ms for 201 M digits, 32 ms at 2^26).  Here the destination range is cut into partitions of
+// 2^log_part entries:
+//   pass A  a block takes SCATTER_TILE digits, counts them per destination partition in shared memory, reserves a
+//           run in every partition's staging area with ONE global atomic per (block, partition) and appends
+//           (position, entry) pairs there -- a few hundred open write frontiers that stay in L2 and leave it as
+//           full lines.  The staging area of partition p is exactly [p << log_part, (p + 1) << log_part): positions
+//           are dense, so no offsets are needed.
+//   pass B  streams the staging area and stores every entry at its position: all stores of a warp fall into one
+//           partition (2^log_part * 4 bytes, L2 resident while it is being filled).
+// The result is the same `entries` array as ScatterRanked's (position = bucket offset + rank).
+constexpr int SCATTER_THREADS = 256;
+constexpr int SCATTER_PER_THREAD = 32;
+constexpr int SCATTER_TILE = SCATTER_THREADS * SCATTER_PER_THREAD;
+constexpr uint32_t SCATTER_MAX_PARTS = 8192;   // shared-memory counters per block
+#if !defined(G16_EMU) && defined(__CUDACC__)
+static __global__ void __launch_bounds__(SCATTER_THREADS) scatter_partition_kernel(const uint32_t *codes, const uint32_t *ranks,
+                                                                            MsmPlan plan, size_t n, const uint32_t *offsets,
+                                                                            uint32_t log_part, uint32_t n_parts,
+                                                                            uint32_t *part_cursor, uint2 *staging) {
+    extern __shared__ uint32_t cnt[];   // n_parts counters, then cursors
+    const size_t total = n * plan.nwin;
+    const size_t tile0 = (size_t)blockIdx.x * SCATTER_TILE;
+    for (uint32_t p = threadIdx.x; p < n_parts; p += SCATTER_THREADS) cnt[p] = 0;
+    __syncthreads();
+    auto position = [&](size_t t, uint32_t code) {
+        uint32_t w = (uint32_t)(t / n);
+        return offsets[(plan.bwin == 1 ? 0u : w) * plan.nb + (code & 0x7fffffffu)] + ranks[t];
+    };
+#pragma unroll 4
+    for (int k = 0; k < SCATTER_PER_THREAD; ++k) {
+        size_t t = tile0 + (size_t)k * SCATTER_THREADS + threadIdx.x;
+        if (t >= total) break;
+        uint32_t code = codes[t];
+        if (code == NO_DIGIT) continue;
+        atomicAdd(&cnt[position(t, code) >> log_part], 1u);
+    }
+    __syncthreads();
+    for (uint32_t p = threadIdx.x; p < n_parts; p += SCATTER_THREADS) {
+        uint32_t c = cnt[p];
+        if (c) cnt[p] = (p << log_part) + atomicAdd(&part_cursor[p], c);
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int k = 0; k < SCATTER_PER_THREAD; ++k) {
+        size_t t = tile0 + (size_t)k * SCATTER_THREADS + threadIdx.x;
+        if (t >= total) break;
+        uint32_t code = codes[t];
+        if (code == NO_DIGIT) continue;
+        uint32_t w = (uint32_t)(t / n), i = (uint32_t)(t % n);
+        uint32_t pos = position(t, code);
+        uint32_t slot = atomicAdd(&cnt[pos >> log_part], 1u);
+        staging[slot] = make_uint2(pos, (w * plan.stride + plan.offset + i) | (code & 0x80000000u));
+    }
+}
+#endif
+// pass B: one thread per staging slot below the entry count (offsets[total buckets])
+struct ScatterFinal {
+    static constexpr int BLOCK = 256;
+    G16_HD static void run(size_t s, const uint32_t *staging, const uint32_t *n_entries, uint32_t *entries) {
+        if (s >= *n_entries) return;
+        entries[staging[2 * s]] = staging[2 * s + 1];
+    }
+};
+
 // ---- work items ------------------------------------------------------------------------------------
 // A work item is a slice [begin, end) of one bucket's entries.  Buckets of up to ITEM_MAX entries are
 // one item; longer ones are split into chunks of about max(ITEM_MAX, sqrt(size)) entries so that a
@@ -158,6 +224,58 @@ struct ItemScatter {
         }
     }
 };
+
+// Device versions of the two kernels above: the 258 length bins are hot addresses (2^21 buckets hit them at 2^24),
+// so a block first bins its 256 buckets in shared memory and then touches every non-empty global bin once.
+#if !defined(G16_EMU) && defined(__CUDACC__)
+static __global__ void __launch_bounds__(256) item_count_kernel(size_t buckets, const uint32_t *offsets, uint32_t item_max,
+                                                                uint32_t *bin_counts) {
+    __shared__ uint32_t cnt[ITEM_BINS];
+    for (uint32_t b = threadIdx.x; b < ITEM_BINS; b += 256) cnt[b] = 0;
+    __syncthreads();
+    size_t g = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (g < buckets) {
+        uint32_t nch, len, bin;
+        item_shape(offsets[g + 1] - offsets[g], item_max, nch, len, bin);
+        atomicAdd(&cnt[bin], nch);
+    }
+    __syncthreads();
+    for (uint32_t b = threadIdx.x; b < ITEM_BINS; b += 256)
+        if (cnt[b]) atomicAdd(&bin_counts[b], cnt[b]);
+}
+static __global__ void __launch_bounds__(256) item_scatter_kernel(size_t buckets, const uint32_t *offsets, uint32_t item_max,
+                                                                  uint32_t *bin_cursor, WorkItem *items, uint32_t *split_list) {
+    __shared__ uint32_t cnt[ITEM_BINS];
+    for (uint32_t b = threadIdx.x; b < ITEM_BINS; b += 256) cnt[b] = 0;
+    __syncthreads();
+    size_t g = (size_t)blockIdx.x * 256 + threadIdx.x;
+    uint32_t begin = 0, size = 0, nch = 0, len = 0, bin = 0, local = 0;
+    if (g < buckets) {
+        begin = offsets[g];
+        size = offsets[g + 1] - begin;
+        item_shape(size, item_max, nch, len, bin);
+        local = atomicAdd(&cnt[bin], nch);
+    }
+    __syncthreads();
+    for (uint32_t b = threadIdx.x; b < ITEM_BINS; b += 256)
+        if (cnt[b]) cnt[b] = atomicAdd(&bin_cursor[b], cnt[b]);   // becomes the block's base in that bin
+    __syncthreads();
+    if (g >= buckets) return;
+    uint32_t pos = cnt[bin] + local;
+    if (nch > 1) {
+        uint32_t k = atomicAdd(&split_list[0], 1u);
+        split_list[1 + 3 * k] = (uint32_t)g;
+        split_list[2 + 3 * k] = pos;
+        split_list[3 + 3 * k] = nch;
+    }
+    for (uint32_t j = 0; j < nch; ++j) {
+        uint32_t b = begin + j * len;
+        uint32_t e = b + len < begin + size ? b + len : begin + size;
+        if (b > begin + size) b = begin + size;
+        items[pos + j] = WorkItem{b, e, (uint32_t)g | (nch > 1 ? SPLIT_FLAG : 0u)};
+    }
+}
+#endif
 
 // packed affine point in HBM: x limbs then y limbs, (0,0) = infinity
 template <class F>
