@@ -14,10 +14,11 @@ void k_scatter_ranked(stream_t s, size_t n, const uint32_t *codes, const uint32_
                       const uint32_t *offsets, uint32_t b_lo, uint32_t b_hi, uint32_t *entries) {
     launch<ScatterRanked>(n * plan.nwin, s, codes, ranks, plan, n, offsets, b_lo, b_hi, entries);
 }
-// partitions of 2^17 entries (512 KB of `entries`) unless that needs more counters than a block holds
+// about 256 partitions of at least 2^20 entries (4 MB of `entries`): a partition stays L2 resident while pass B fills
+// it, and a block's tile leaves runs of ~16 pairs per partition, so its staging writes coalesce
 uint32_t k_scatter_log_part(size_t max_entries) {
-    uint32_t lp = 17;
-    while (((max_entries >> lp) + 1) > SCATTER_MAX_PARTS) ++lp;
+    uint32_t lp = 20;
+    while ((max_entries >> lp) + 1 > 256) ++lp;
     return lp;
 }
 void k_scatter_partitioned(stream_t s, size_t n, const uint32_t *codes, const uint32_t *ranks, MsmPlan plan,
@@ -29,7 +30,8 @@ void k_scatter_partitioned(stream_t s, size_t n, const uint32_t *codes, const ui
     size_t total = n * plan.nwin;
     size_t blocks = (total + SCATTER_TILE - 1) / SCATTER_TILE;
     G16_CUDA_CHECK(cudaMemsetAsync(part_cursor, 0, n_parts * sizeof(uint32_t), s));
-    scatter_partition_kernel<<<(unsigned)blocks, SCATTER_THREADS, n_parts * sizeof(uint32_t), s>>>(
+    size_t smem = (size_t)SCATTER_TILE * sizeof(uint2) + 3 * (size_t)n_parts * sizeof(uint32_t);
+    scatter_partition_kernel<<<(unsigned)blocks, SCATTER_THREADS, smem, s>>>(
         codes, ranks, plan, n, offsets, log_part, n_parts, part_cursor, reinterpret_cast<uint2 *>(staging));
     G16_CUDA_CHECK(cudaGetLastError());
     note_launch();

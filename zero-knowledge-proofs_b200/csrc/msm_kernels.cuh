@@ -118,47 +118,99 @@ struct ScatterRanked {
 //           partition (2^log_part * 4 bytes, L2 resident while it is being filled).
 // The result is the same `entries` array as ScatterRanked's (position = bucket offset + rank).
 constexpr int SCATTER_THREADS = 256;
-constexpr int SCATTER_PER_THREAD = 32;
+constexpr int SCATTER_PER_THREAD = 16;
 constexpr int SCATTER_TILE = SCATTER_THREADS * SCATTER_PER_THREAD;
-constexpr uint32_t SCATTER_MAX_PARTS = 8192;   // shared-memory counters per block
+constexpr uint32_t SCATTER_MAX_PARTS = 1024;   // shared-memory counters per block
 #if !defined(G16_EMU) && defined(__CUDACC__)
+// shared memory: SCATTER_TILE (position, entry) pairs sorted by partition, then 3 x n_parts words
 static __global__ void __launch_bounds__(SCATTER_THREADS) scatter_partition_kernel(const uint32_t *codes, const uint32_t *ranks,
                                                                             MsmPlan plan, size_t n, const uint32_t *offsets,
                                                                             uint32_t log_part, uint32_t n_parts,
                                                                             uint32_t *part_cursor, uint2 *staging) {
-    extern __shared__ uint32_t cnt[];   // n_parts counters, then cursors
+    extern __shared__ uint2 tile_buf[];
+    uint32_t *cnt = reinterpret_cast<uint32_t *>(tile_buf + SCATTER_TILE);   // digits per partition, then fill cursor
+    uint32_t *first = cnt + n_parts;                                        // first tile slot of the partition
+    uint32_t *gbase = first + n_parts;                                      // first staging slot reserved for this block
     const size_t total = n * plan.nwin;
     const size_t tile0 = (size_t)blockIdx.x * SCATTER_TILE;
     for (uint32_t p = threadIdx.x; p < n_parts; p += SCATTER_THREADS) cnt[p] = 0;
     __syncthreads();
-    auto position = [&](size_t t, uint32_t code) {
-        uint32_t w = (uint32_t)(t / n);
-        return offsets[(plan.bwin == 1 ? 0u : w) * plan.nb + (code & 0x7fffffffu)] + ranks[t];
+    // positions of this thread's digits stay in registers (0xffffffff: no digit), the sign bits in one word
+    uint32_t pos[SCATTER_PER_THREAD], signs = 0;
+    // (window, index) of a flattened digit number without a 64-bit division per digit: one per thread, then steps
+    const uint32_t w0 = (uint32_t)(tile0 / n);
+    const size_t r0 = tile0 - (size_t)w0 * n;
+    auto window_index = [&](int k, uint32_t &w, uint32_t &i) {
+        size_t r = r0 + (size_t)k * SCATTER_THREADS + threadIdx.x;
+        w = w0;
+        while (r >= n) { r -= n; ++w; }
+        i = (uint32_t)r;
     };
-#pragma unroll 4
+#pragma unroll
     for (int k = 0; k < SCATTER_PER_THREAD; ++k) {
         size_t t = tile0 + (size_t)k * SCATTER_THREADS + threadIdx.x;
-        if (t >= total) break;
-        uint32_t code = codes[t];
-        if (code == NO_DIGIT) continue;
-        atomicAdd(&cnt[position(t, code) >> log_part], 1u);
+        uint32_t code = t < total ? codes[t] : NO_DIGIT;
+        pos[k] = 0xffffffffu;
+        if (code != NO_DIGIT) {
+            uint32_t w, i;
+            window_index(k, w, i);
+            pos[k] = offsets[(plan.bwin == 1 ? 0u : w) * plan.nb + (code & 0x7fffffffu)] + ranks[t];
+            signs |= (code >> 31) << k;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < SCATTER_PER_THREAD; ++k)
+        if (pos[k] != 0xffffffffu) atomicAdd(&cnt[pos[k] >> log_part], 1u);
+    __syncthreads();
+    // exclusive prefix of the counters (n_parts <= 1024: four per thread, warp scan, warp totals through `gbase`)
+    {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        uint32_t v[4], sum = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            uint32_t p = threadIdx.x * 4 + j;
+            v[j] = p < n_parts ? cnt[p] : 0u;
+            sum += v[j];
+        }
+        uint32_t incl = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += o;
+        }
+        __shared__ uint32_t warp_tot[SCATTER_THREADS / 32];
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();
+        uint32_t base = 0;
+        for (int q = 0; q < warp; ++q) base += warp_tot[q];
+        uint32_t run = base + incl - sum;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            uint32_t p = threadIdx.x * 4 + j;
+            if (p < n_parts) {
+                first[p] = run;
+                gbase[p] = v[j] ? (p << log_part) + atomicAdd(&part_cursor[p], v[j]) : 0u;
+                cnt[p] = run;   // fill cursor
+            }
+            run += v[j];
+        }
     }
     __syncthreads();
-    for (uint32_t p = threadIdx.x; p < n_parts; p += SCATTER_THREADS) {
-        uint32_t c = cnt[p];
-        if (c) cnt[p] = (p << log_part) + atomicAdd(&part_cursor[p], c);
-    }
-    __syncthreads();
-#pragma unroll 4
+#pragma unroll
     for (int k = 0; k < SCATTER_PER_THREAD; ++k) {
-        size_t t = tile0 + (size_t)k * SCATTER_THREADS + threadIdx.x;
-        if (t >= total) break;
-        uint32_t code = codes[t];
-        if (code == NO_DIGIT) continue;
-        uint32_t w = (uint32_t)(t / n), i = (uint32_t)(t % n);
-        uint32_t pos = position(t, code);
-        uint32_t slot = atomicAdd(&cnt[pos >> log_part], 1u);
-        staging[slot] = make_uint2(pos, (w * plan.stride + plan.offset + i) | (code & 0x80000000u));
+        if (pos[k] == 0xffffffffu) continue;
+        uint32_t w, i;
+        window_index(k, w, i);
+        uint32_t slot = atomicAdd(&cnt[pos[k] >> log_part], 1u);
+        tile_buf[slot] = make_uint2(pos[k], (w * plan.stride + plan.offset + i) | (((signs >> k) & 1u) << 31));
+    }
+    __syncthreads();
+    // linear write-out: consecutive threads carry consecutive members of a partition's run
+    const uint32_t filled = first[n_parts - 1] + (cnt[n_parts - 1] - first[n_parts - 1]);
+    for (uint32_t j = threadIdx.x; j < filled; j += SCATTER_THREADS) {
+        uint2 e = tile_buf[j];
+        uint32_t p = e.x >> log_part;
+        staging[gbase[p] + (j - first[p])] = e;
     }
 }
 #endif
