@@ -228,8 +228,16 @@ inline uint32_t affine_rounds_for(size_t entries, size_t buckets) {
 
 constexpr size_t SCATTER_TWO_PASS_BYTES = (size_t)96 << 20;   // `entries` larger than this (~L2) are scattered in two passes
 constexpr uint32_t REDUCE_LOG_L = 5;
-constexpr size_t TILE_LEVEL_MAX = 1u << 16;   // levels with at most this many entries run block-cooperatively
-constexpr size_t THREAD_LEVEL_GROUPS = 1u << 16;   // groups a thread level aims to leave behind
+// Levels with at most 2^tile_max_log2 entries run block-cooperatively; a thread level aims to leave 2^groups_log2 groups
+// behind.  Measured on B200 (profiles/README.md run 19): 15 / 15 is best up to 2^20 buckets (reduce 1.14 -> 0.99 ms at 2^19
+// buckets), 17 / 16 beyond (3.07 -> 3.00 ms at 2^21).  G16_REDUCE_GROUPS_LOG2 / G16_TILE_MAX_LOG2 override for tuning runs.
+inline void reduce_split(size_t buckets, size_t &tile_level_max, size_t &thread_level_groups) {
+    static const int env_g = getenv("G16_REDUCE_GROUPS_LOG2") ? atoi(getenv("G16_REDUCE_GROUPS_LOG2")) : 0;
+    static const int env_t = getenv("G16_TILE_MAX_LOG2") ? atoi(getenv("G16_TILE_MAX_LOG2")) : 0;
+    bool big = buckets > ((size_t)1 << 20);
+    thread_level_groups = (size_t)1 << (env_g ? env_g : (big ? 17 : 15));
+    tile_level_max = (size_t)1 << (env_t ? env_t : (big ? 16 : 15));
+}
 
 // One MSM on one device, asynchronous on dv.stream.
 //   pts        : packed affine bases on this device (n points)
@@ -334,6 +342,8 @@ void msm_run(Device &dv, const BasesShard &sh, const uint32_t *d_scalars, size_t
     uint32_t n_in = plan.nb, shift = 0;
     int flip = 0;
     constexpr size_t PWORDS = 4 * FieldWords<F>::N;
+    size_t TILE_LEVEL_MAX, THREAD_LEVEL_GROUPS;
+    reduce_split((size_t)plan.bwin * plan.nb, TILE_LEVEL_MAX, THREAD_LEVEL_GROUPS);
     while (n_in > 1) {
         uint32_t n_out, log_l;
         if ((size_t)plan.bwin * n_in > TILE_LEVEL_MAX) {

@@ -78,6 +78,15 @@ void k_window_combine(stream_t s, const uint32_t *X, const uint32_t *Y, const ui
 }
 template <class F>
 void k_partial_combine(stream_t s, const uint32_t *partials, uint32_t k, uint32_t *out_xyzz, uint32_t *out_aff) {
+#ifndef G16_EMU
+    if (k >= 4) {   // a handful of partials (one per GPU): warp-cooperative fold
+        size_t smem = (size_t)8 * (4 * F::N + 1) * sizeof(uint32_t);
+        partial_combine_warp_kernel<F><<<1, 32, smem, s>>>(partials, k, out_xyzz, out_aff);
+        G16_CUDA_CHECK(cudaGetLastError());
+        note_launch();
+        return;
+    }
+#endif
     launch<PartialCombine<F>>(1, s, partials, k, out_xyzz, out_aff);
 }
 template <class F>

@@ -658,7 +658,7 @@ struct WindowCombine {
                            uint32_t *out_xyzz, uint32_t *out_aff) {
         XYZZ<F> acc = XYZZ<F>::inf();
         for (uint32_t w = nwin; w-- > 0;) {
-            for (uint32_t s = 0; s < c; ++s) xyzz_dbl_call(acc);
+            if (!acc.is_inf()) for (uint32_t s = 0; s < c; ++s) xyzz_dbl_call(acc);
             XYZZ<F> x = load_xyzz<F>(X, w);
             xyzz_add_call(acc, x);
             if (Y) {
@@ -699,6 +699,41 @@ struct PartialCombine {
         }
     }
 };
+
+// The same fold on one warp (device build): eight quads take the partials round-robin with the 4-lane cooperative
+// addition, a three-step tree through shared memory joins them, lane 0 converts to affine.  k = 8 (one box of GPUs):
+// 1 + 3 cooperative additions instead of 8 serial ones in front of the inversion.
+#if !defined(G16_EMU) && defined(__CUDACC__)
+template <class F>
+__global__ void __launch_bounds__(32) partial_combine_warp_kernel(const uint32_t *partials, uint32_t k, uint32_t *out_xyzz,
+                                                                  uint32_t *out_aff) {
+    extern __shared__ uint32_t sm[];
+    const int e = threadIdx.x >> 2, q = threadIdx.x & 3;
+    XYZZ<F> acc = XYZZ<F>::inf();
+#pragma unroll 1
+    for (uint32_t i0 = 0; i0 < k; i0 += 8) {
+        XYZZ<F> p = i0 + e < k ? load_xyzz<F>(partials, i0 + e) : XYZZ<F>::inf();
+        xyzz_add_quad(acc, p, q);
+    }
+#pragma unroll 1
+    for (int d = 4; d >= 1; d >>= 1) {
+        tile_put<F>(sm, e, q, acc);
+        __syncwarp();
+        XYZZ<F> t = e < d ? tile_get<F>(sm, e + d) : XYZZ<F>::inf();
+        xyzz_add_quad(acc, t, q);
+        __syncwarp();
+    }
+    if (threadIdx.x == 0) {
+        if (out_xyzz) store_xyzz<F>(out_xyzz, 0, acc);
+        if (out_aff) {
+            Affine<F> a = xyzz_to_affine(acc);
+            const uint32_t *s = reinterpret_cast<const uint32_t *>(&a);
+            for (int j = 0; j < 2 * F::N; ++j) out_aff[j] = s[j];
+            out_aff[2 * F::N] = acc.is_inf() ? 1u : 0u;
+        }
+    }
+}
+#endif
 
 // Precomputed multiples for resident bases: table[w * n + i] = 2^(c w) * P_i as affine points, so that
 // digit w of scalar i adds table[w][i] into ONE shared bucket set -- the Horner fold over windows and
