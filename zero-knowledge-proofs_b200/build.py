@@ -72,12 +72,16 @@ def build(force: bool = False, jobs: int | None = None, verbose: bool = False) -
 
 
 def build_tools(force: bool = False) -> str:
-    """lib/imad_peak: the integer-pipe roofline microbenchmark bench.py runs before the timed region."""
-    src = os.path.join(HERE, "tools", "imad_peak.cu")
-    out = os.path.join(LIBDIR, "imad_peak")
-    if force or not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(src), _newest_header()):
-        subprocess.run([NVCC] + ARCH + ["-O3", "-std=c++17", "-lineinfo", "-o", out, src], check=True)
-    return out
+    """lib/imad_peak: the integer-pipe roofline microbenchmark bench.py runs before the timed region;
+    lib/dfma_peak: the FP64-pipe companion quoted in DESIGN.md."""
+    first = None
+    for name in ("imad_peak", "dfma_peak"):
+        src = os.path.join(HERE, "tools", name + ".cu")
+        out = os.path.join(LIBDIR, name)
+        if force or not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(src), _newest_header()):
+            subprocess.run([NVCC] + ARCH + ["-O3", "-std=c++17", "-lineinfo", "-o", out, src], check=True)
+        first = first or out
+    return first
 
 
 if __name__ == "__main__":
