@@ -112,6 +112,14 @@ inline void set_device(int id) {
 #endif
 }
 
+// host-scalar MSMs of at least H2D_PIPE_MIN scalars copy them in H2D_PIPE_CHUNKS pieces on lane H2D_PIPE_LANE
+#ifndef G16_EMU
+constexpr size_t H2D_PIPE_MIN = (size_t)1 << 20;
+#else
+constexpr size_t H2D_PIPE_MIN = 64;   // the emulation tests walk the chunk offsets on small inputs
+#endif
+constexpr size_t H2D_PIPE_CHUNKS = 8;
+constexpr int H2D_PIPE_LANE = 7;   // lanes 0-4: prove schedule, 8+: chunk pipelines
 constexpr size_t CHUNK_MIN_SCALARS = ~(size_t)0;   // chunked host-scalar pipeline: off by default
 constexpr size_t H2D_CHUNKS = 4;
 constexpr int CHUNK_LANE_BASE = 8;                // lanes 8.. are reserved for chunk pipelines
@@ -243,9 +251,13 @@ inline void reduce_split(size_t buckets, size_t &tile_level_max, size_t &thread_
 //   pts        : packed affine bases on this device (n points)
 //   d_scalars  : n x 8 u32 on this device
 //   d_out_xyzz : 4*FieldWords<F>::N words (may be null), d_out_aff : 2*FieldWords<F>::N + 1 words (may be null)
+// h_scalars (optional): the scalars still live on the host; they are copied into d_stage (= d_scalars) here, in chunks on a
+// second stream, each chunk's digit decomposition starting as soon as it has arrived -- the first stage of the pipeline
+// hides under the H2D copy (1.8 ms of a 9.7 ms copy at 2^24).
 template <class F>
 void msm_run(Device &dv, const BasesShard &sh, const uint32_t *d_scalars, size_t n, bool mont, unsigned c_override,
-             uint32_t *d_out_xyzz, uint32_t *d_out_aff, size_t first = 0) {
+             uint32_t *d_out_xyzz, uint32_t *d_out_aff, size_t first = 0, const uint64_t *h_scalars = nullptr,
+             uint32_t *d_stage = nullptr) {
     // bases [first, first + n) of the shard
     const uint32_t *pts = sh.table ? sh.table : sh.pts;
     stream_t s = dv.stream;
@@ -269,7 +281,20 @@ void msm_run(Device &dv, const BasesShard &sh, const uint32_t *d_scalars, size_t
     uint32_t *codes = ws.codes.as<uint32_t>(max_entries);
     static const bool ranked = getenv("G16_ATOMIC_SCATTER") == nullptr;   // default: rank-based scatter
     uint32_t *ranks = ranked ? ws.ranks.as<uint32_t>(max_entries) : nullptr;
-    k_digit_decompose(s, n, d_scalars, mont, plan, counts, codes, ranks);
+    if (h_scalars && n >= H2D_PIPE_MIN) {
+        Device &cp = lane_of(dv, H2D_PIPE_LANE);
+        stream_wait(cp.stream, s);   // earlier work on s may still read the staging buffer
+        for (size_t k = 0; k < H2D_PIPE_CHUNKS; ++k) {
+            size_t lo = n * k / H2D_PIPE_CHUNKS, hi = n * (k + 1) / H2D_PIPE_CHUNKS;
+            if (hi == lo) continue;
+            copy_h2d(d_stage + lo * 8, h_scalars + lo * 4, (hi - lo) * 32, cp.stream);
+            stream_wait(s, cp.stream);
+            k_digit_decompose(s, n, d_scalars, mont, plan, counts, codes, ranks, lo, hi - lo);
+        }
+    } else {
+        if (h_scalars) copy_h2d(d_stage, h_scalars, n * 32, s);
+        k_digit_decompose(s, n, d_scalars, mont, plan, counts, codes, ranks);
+    }
     dv.timer.mark(1, s);
     // 2. bucket offsets (exclusive scan; offsets[total] = number of entries) and the work-item list
     //    (bucket slices ordered by length, longest first)
@@ -480,11 +505,11 @@ void msm_launch(Context *ctx, const Bases *bases, const uint64_t *scalars, size_
         size_t chunks = cnt >= ctx->chunk_min ? H2D_CHUNKS : 1;
         if (chunks == 1) {
             uint32_t *d_sc = dv.ws.scalars.as<uint32_t>(cnt * 8 + 8);
-            copy_h2d(d_sc, scalars + lo * 4, cnt * 32, dv.stream);
+            const uint64_t *h_sc = scalars + lo * 4;   // copied inside msm_run, overlapped with the digit decomposition
             if (nsh == 1) {
-                msm_run<F>(dv, sh, d_sc, cnt, true, ctx->c_override, user_xyzz, user_out ? user_aff : d_out + PW, lo - sh.begin);
+                msm_run<F>(dv, sh, d_sc, cnt, true, ctx->c_override, user_xyzz, user_out ? user_aff : d_out + PW, lo - sh.begin, h_sc, d_sc);
             } else {
-                msm_run<F>(dv, sh, d_sc, cnt, true, ctx->c_override, d_out, nullptr, lo - sh.begin);
+                msm_run<F>(dv, sh, d_sc, cnt, true, ctx->c_override, d_out, nullptr, lo - sh.begin, h_sc, d_sc);
                 copy_d2h(l0.host_partials.data() + k * PW, d_out, PW * 4, dv.stream);
             }
         } else {

@@ -7,8 +7,9 @@ static std::atomic<unsigned long long> g_launches{0};
 void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 unsigned long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
 void k_digit_decompose(stream_t s, size_t n, const uint32_t *scalars, bool mont, MsmPlan plan, uint32_t *counts,
-                        uint32_t *codes, uint32_t *ranks) {
-    launch<DigitDecompose>(n, s, scalars, mont, plan, n, counts, codes, ranks);
+                        uint32_t *codes, uint32_t *ranks, size_t i0, size_t cnt) {
+    if (cnt == ~(size_t)0) cnt = n - i0;
+    launch<DigitDecompose>(cnt, s, scalars, mont, plan, n, counts, codes, ranks, i0);
 }
 void k_scatter_ranked(stream_t s, size_t n, const uint32_t *codes, const uint32_t *ranks, MsmPlan plan,
                       const uint32_t *offsets, uint32_t b_lo, uint32_t b_hi, uint32_t *entries) {

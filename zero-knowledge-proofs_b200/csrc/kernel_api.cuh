@@ -28,8 +28,9 @@ template <> struct FieldWords<Fq> { static constexpr size_t N = 12; static const
 template <> struct FieldWords<Fq2> { static constexpr size_t N = 24; static constexpr int group = 2; };
 
 // scalars -> bucket histogram / bucket-ordered entries
+// digits of scalars [i0, i0 + cnt) of an n-scalar call
 void k_digit_decompose(stream_t s, size_t n, const uint32_t *scalars, bool mont, MsmPlan plan, uint32_t *counts,
-                        uint32_t *codes, uint32_t *ranks);
+                        uint32_t *codes, uint32_t *ranks, size_t i0 = 0, size_t cnt = ~(size_t)0);
 void k_scatter_ranked(stream_t s, size_t n, const uint32_t *codes, const uint32_t *ranks, MsmPlan plan,
                       const uint32_t *offsets, uint32_t b_lo, uint32_t b_hi, uint32_t *entries);
 // two-pass scatter through a staging area of (position, entry) pairs (device build only; see msm_kernels.cuh):

@@ -52,8 +52,10 @@ constexpr uint32_t NO_DIGIT = 0xffffffffu;
 // array codes[w * n + i] (window-major so that the scatter pass below streams it coalesced).
 struct DigitDecompose {
     static constexpr int BLOCK = 256;
-    G16_HD static void run(size_t i, const uint32_t *scalars, bool mont, MsmPlan plan, size_t n, uint32_t *counts,
-                           uint32_t *codes, uint32_t *ranks) {
+    // the launch covers scalars [i0, i0 + threads) of the n of the call (host scalars arrive in chunks)
+    G16_HD static void run(size_t t, const uint32_t *scalars, bool mont, MsmPlan plan, size_t n, uint32_t *counts,
+                           uint32_t *codes, uint32_t *ranks, size_t i0) {
+        const size_t i = t + i0;
         uint32_t k[8];
         load_scalar(scalars, i, mont, k);
         DigitIter it(k, plan.c);
