@@ -54,7 +54,8 @@ def test_prove_multi_device_random_key(gpu_ctx, oracle, gens):
     zero scalars, with and without H."""
     import groth16_cuda
     ndev = gpu_ctx.lib.g16_device_count()
-    for devs in ([0, 0], list(range(min(ndev, 8))) if ndev > 1 else [0, 0, 0]):
+    # five shards: the fold of the partial sums takes the warp-cooperative path (k >= 4) in G1 and G2
+    for devs in ([0, 0], [0, 0, 0, 0, 0], list(range(min(ndev, 8))) if ndev > 1 else [0, 0, 0]):
         ctx = groth16_cuda.Context(devices=devs)
         try:
             prove_cases.check_random_key(ctx, gpu_ctx, oracle, gens, n=3001, seed=len(devs))
