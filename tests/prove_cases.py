@@ -63,6 +63,15 @@ def check_config1(ctx, golden=None):
         assert ref.verify(vk, got, w[1:npub + 1]) is verdict, name
         if verdict:   # a wrong public input must not verify (test_invalid_proof, lib.rs:483-511)
             assert ref.verify(vk, got, [w[1] + 1]) is False
+        # the verifier's own MSM (Verifier::verify, lib.rs:330-340: ic[0] + sum x_i ic[i+1], a 2-term call of
+        # multi_scalar_mult_g1) through the engine: same point as the model's
+        pub = [ref.t64(x) for x in w[1:npub + 1]]
+        terms = [(1, vk["ic_g1"][0])] + [(x, vk["ic_g1"][i + 1]) for i, x in enumerate(pub) if x]
+        exp_ic = bls.G1.msm_naive([p for _, p in terms], [k for k, _ in terms])
+        pts = np.array([bls.g1_to_mont(p)[0] for _, p in terms], dtype=np.uint64).reshape(-1, 12)
+        inf = np.array([bls.g1_to_mont(p)[1] for _, p in terms], dtype=np.uint8)
+        ic_xy, ic_inf = ctx.multi_scalar_mult_g1(fr_arr([k for k, _ in terms]), pts, inf)
+        assert bls.g1_from_mont(list(ic_xy), ic_inf) == exp_ic, name
         out[name] = ref.proof_to_bytes(got).hex()
         if golden is not None:
             assert golden[name] == out[name], name
