@@ -303,8 +303,12 @@ void msm_run(Device &dv, const BasesShard &sh, const uint32_t *d_scalars, size_t
     uint32_t *offsets = counts;
     size_t nbins = k_item_bins();
     // longest work item: 256 additions when the call is large (a serial walk of 256 is noise), shorter
-    // when it is small and the longest item would set the kernel's duration
-    uint32_t item_max = (uint32_t)std::min<size_t>(k_item_max(), std::max<size_t>(64, max_entries >> 17));
+    // when it is small and the longest item would set the kernel's duration.  Floor 16 (was 64): at 2^16 / 2^18 pairs the
+    // 2^15 buckets alone are too few threads, cutting them into chunks of <= 16 / 32 entries takes the accumulation from
+    // 0.79 to 0.70 ms and from 2.39 to 2.02 ms (profiles/README.md run 23); G16_ITEM_FLOOR / G16_ITEM_SHIFT for tuning runs
+    static const size_t item_floor = getenv("G16_ITEM_FLOOR") ? (size_t)atoi(getenv("G16_ITEM_FLOOR")) : 16;
+    static const unsigned item_shift = getenv("G16_ITEM_SHIFT") ? (unsigned)atoi(getenv("G16_ITEM_SHIFT")) : 17;
+    uint32_t item_max = (uint32_t)std::min<size_t>(k_item_max(), std::max<size_t>(item_floor, max_entries >> item_shift));
     uint32_t *bins = ws.bins.as<uint32_t>(2 * (nbins + 1));
     uint32_t *bin_cursor = bins + nbins + 1;
     dev_memset(bins, 0, (nbins + 1) * sizeof(uint32_t), s);
