@@ -278,6 +278,85 @@ struct Fp {
         final_sub(r.l);
         return r;
     }
+    // ---- wide product and separate reduction (lazy reduction in Fq2, see fq2.cuh) ---------------------------------
+    // t[0 .. 2N) = a * b, no reduction; a, b < 2^(32 N).  Same two 64-bit aligned accumulators as the squaring above:
+    // ce[k] holds word k of the partial products with i + j even, co[k] word k + 1 of those with i + j odd.
+    G16_HD static void mul_wide(const uint32_t *a, const uint32_t *b, uint32_t *t) {
+        uint32_t ce[2 * N], co[2 * N];
+#pragma unroll
+        for (int k = 0; k < 2 * N; ++k) { ce[k] = 0; co[k] = 0; }
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            // j of the parity of i: i + j even -> ce[i + j]
+            {
+                int j = i & 1;
+                ce[i + j] = mad_lo_cc(a[j], b[i], ce[i + j]);
+                ce[i + j + 1] = madc_hi_cc(a[j], b[i], ce[i + j + 1]);
+#pragma unroll
+                for (j += 2; j < N; j += 2) {
+                    ce[i + j] = madc_lo_cc(a[j], b[i], ce[i + j]);
+                    ce[i + j + 1] = madc_hi_cc(a[j], b[i], ce[i + j + 1]);
+                }
+                if (i + j < 2 * N) ce[i + j] = addc(ce[i + j], 0u);   // j = first index past the chain
+            }
+            // j of the other parity: i + j odd -> co[i + j - 1]
+            {
+                int j = (i & 1) ^ 1;
+                co[i + j - 1] = mad_lo_cc(a[j], b[i], co[i + j - 1]);
+                co[i + j] = madc_hi_cc(a[j], b[i], co[i + j]);
+#pragma unroll
+                for (j += 2; j < N; j += 2) {
+                    co[i + j - 1] = madc_lo_cc(a[j], b[i], co[i + j - 1]);
+                    co[i + j] = madc_hi_cc(a[j], b[i], co[i + j]);
+                }
+                if (i + j - 1 < 2 * N) co[i + j - 1] = addc(co[i + j - 1], 0u);
+            }
+        }
+        t[0] = ce[0];
+        t[1] = add_cc(ce[1], co[0]);
+#pragma unroll
+        for (int k = 2; k < 2 * N - 1; ++k) t[k] = addc_cc(ce[k], co[k - 1]);
+        t[2 * N - 1] = addc(ce[2 * N - 1], co[2 * N - 2]);
+    }
+    // T * R^-1 mod p for a 2N-word T < p * R, fully reduced: redc of the low half (product-free CIOS rounds) + high half
+    G16_HD static Fp redc_wide(const uint32_t *t) {
+        uint32_t ev[N], od[N];
+#pragma unroll
+        for (int k = 0; k < N; ++k) { ev[k] = t[k]; od[k] = 0; }
+        redc_round<true>(ev, od);
+        redc_round<false>(od, ev);
+#pragma unroll
+        for (int i = 2; i < N; i += 2) {
+            redc_round<false>(ev, od);
+            redc_round<false>(od, ev);
+        }
+        Fp r;
+        r.l[0] = add_cc(ev[0], od[1]);
+#pragma unroll
+        for (int i = 1; i < N - 1; ++i) r.l[i] = addc_cc(ev[i], od[i + 1]);
+        r.l[N - 1] = addc(ev[N - 1], 0u);
+        final_sub(r.l);                       // redc(t_lo) <= p
+        r.l[0] = add_cc(r.l[0], t[N]);
+#pragma unroll
+        for (int i = 1; i < N - 1; ++i) r.l[i] = addc_cc(r.l[i], t[N + i]);
+        r.l[N - 1] = addc(r.l[N - 1], t[2 * N - 1]);
+        final_sub(r.l);
+        return r;
+    }
+    // x -= y over 2N words; returns the borrow (all ones when x < y)
+    G16_HD static uint32_t sub_wide(uint32_t *x, const uint32_t *y) {
+        x[0] = sub_cc(x[0], y[0]);
+#pragma unroll
+        for (int i = 1; i < 2 * N; ++i) x[i] = subc_cc(x[i], y[i]);
+        return subc(0u, 0u);
+    }
+    // a + b without reduction (a, b < p: the sum fits the N words because p has spare top bits)
+    G16_HD static void add_noreduce(const uint32_t *a, const uint32_t *b, uint32_t *r) {
+        r[0] = add_cc(a[0], b[0]);
+#pragma unroll
+        for (int i = 1; i < N - 1; ++i) r[i] = addc_cc(a[i], b[i]);
+        r[N - 1] = addc(a[N - 1], b[N - 1]);
+    }
     // one reduction round on value = E + O * 2^32; on exit E[0] == 0 (mod 2^32), caller swaps roles
     template <bool FIRST>
     G16_HD static void redc_round(uint32_t *E, uint32_t *O) {

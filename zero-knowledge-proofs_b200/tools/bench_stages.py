@@ -15,12 +15,13 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--bits", type=int, default=255)
     ap.add_argument("--no-precompute", action="store_true")
+    ap.add_argument("--lib", default=None, help="alternative build of the library (A/B experiments)")
     a = ap.parse_args()
     import torch, bls12_381 as bls, cpu_oracle as oracle, groth16_cuda
     oracle.build()
     n = 1 << a.log_n
     dev = torch.device("cuda:0")
-    ctx = groth16_cuda.Context([0])
+    ctx = groth16_cuda.Context([0], lib_path=a.lib)
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
     lib = ctx.lib
     lib.g16_ctx_enable_stage_timing.argtypes = [ctypes.c_void_p, ctypes.c_int]
