@@ -62,6 +62,36 @@ __global__ void __launch_bounds__(256) k_mixed(double *out, double a, double b, 
     if (s == 0.12345) out[0] = s;
 }
 
+// The inner step of a double-precision-limb multiplication as Emmart et al. formulate it: per 52 x 52 limb product
+//   hi = fma_rz(a, b, 2^104);  s = (2^104 + 2^52) - hi;  lo = fma_rz(a, b, s)
+// and the two results are accumulated as raw 64-bit integers (the exponent bits are constant and come off at the end).
+// 2 DFMA + 1 DADD + 2 integer 64-bit adds per product; a 381-bit Montgomery multiplication needs 128 of them.
+__global__ void __launch_bounds__(256) k_dpf_product(double *out, double a0, double b0, int iters) {
+    const double C1 = 20282409603651670423947251286016.0;                    // 2^104
+    const double C2 = 20282409603651670423947251286016.0 + 4503599627370496.0;   // 2^104 + 2^52
+    double a[4], b[4];
+    long long acc_hi[4], acc_lo[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { a[i] = a0 + threadIdx.x + i; b[i] = b0 + i; acc_hi[i] = 0; acc_lo[i] = 0; }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < INNER; ++k)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                double hi, sdiff, lo;
+                asm volatile("fma.rz.f64 %0, %1, %2, %3;" : "=d"(hi) : "d"(a[i]), "d"(b[i]), "d"(C1));
+                asm volatile("sub.rz.f64 %0, %1, %2;" : "=d"(sdiff) : "d"(C2), "d"(hi));
+                asm volatile("fma.rz.f64 %0, %1, %2, %3;" : "=d"(lo) : "d"(a[i]), "d"(b[i]), "d"(sdiff));
+                asm volatile("add.s64 %0, %0, %1;" : "+l"(acc_hi[i]) : "l"(__double_as_longlong(hi)));
+                asm volatile("add.s64 %0, %0, %1;" : "+l"(acc_lo[i]) : "l"(__double_as_longlong(lo)));
+            }
+    }
+    long long s = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) s ^= acc_hi[i] ^ acc_lo[i];
+    if (s == 0x123456789ll) out[0] = (double)s;
+}
+
 template <class L>
 static double time_ms(L launch) {
     cudaEvent_t e0, e1;
@@ -89,11 +119,15 @@ int main(int argc, char **argv) {
     double ms_d = time_ms([&] { k_dfma<<<blocks, threads>>>(d_out, 1.0000001, 0.5, iters); });
     double ms_w = time_ms([&] { k_wide<<<blocks, threads>>>(d_out, 3u, 5u, iters); });
     double ms_m = time_ms([&] { k_mixed<<<blocks, threads>>>(d_out, 1.0000001, 0.5, 3u, 5u, iters); });
+    double ms_p = time_ms([&] { k_dpf_product<<<blocks, threads>>>(d_out, 1125899906842624.0, 2251799813685248.0, iters); });
+    double dpf_products = total * 4 / (ms_p * 1e-3);
     printf("{\"device\": \"%s\", \"sms\": %d, \"dfma_per_s\": %.6e, \"imad_wide_per_s\": %.6e, "
            "\"mixed_dfma_per_s\": %.6e, \"mixed_imad_wide_per_s\": %.6e, \"ms\": {\"dfma\": %.3f, \"imad_wide\": %.3f, \"mixed\": %.3f}, "
-           "\"bits2_per_s\": {\"dfma_52x52_two_fma\": %.4e, \"imad_wide_32x32\": %.4e}}\n",
+           "\"bits2_per_s\": {\"dfma_52x52_two_fma\": %.4e, \"imad_wide_32x32\": %.4e}, "
+           "\"dpf_limb_products_per_s\": %.6e, \"dpf_ms\": %.3f, \"dpf_fq_mul_per_s_at_128_products\": %.4e}\n",
            prop.name, sms, total * 8 / (ms_d * 1e-3), total * 8 / (ms_w * 1e-3), total * 4 / (ms_m * 1e-3), total * 4 / (ms_m * 1e-3),
-           ms_d, ms_w, ms_m, total * 8 / (ms_d * 1e-3) / 2 * 2704, total * 8 / (ms_w * 1e-3) * 1024);
+           ms_d, ms_w, ms_m, total * 8 / (ms_d * 1e-3) / 2 * 2704, total * 8 / (ms_w * 1e-3) * 1024, dpf_products, ms_p,
+           dpf_products / 128.0);
     cudaFree(d_out);
     return 0;
 }
