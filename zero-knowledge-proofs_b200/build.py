@@ -73,9 +73,9 @@ def build(force: bool = False, jobs: int | None = None, verbose: bool = False) -
 
 def build_tools(force: bool = False) -> str:
     """lib/imad_peak: the integer-pipe roofline microbenchmark bench.py runs before the timed region;
-    lib/dfma_peak: the FP64-pipe companion quoted in DESIGN.md."""
+    lib/dfma_peak, lib/dpf_mul_bench: the FP64-pipe companions quoted in DESIGN.md."""
     first = None
-    for name in ("imad_peak", "dfma_peak"):
+    for name in ("imad_peak", "dfma_peak", "dpf_mul_bench"):
         src = os.path.join(HERE, "tools", name + ".cu")
         out = os.path.join(LIBDIR, name)
         if force or not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(src), _newest_header()):
