@@ -118,6 +118,43 @@ struct Dpf {
         bool ge = !borrow || (prev_hi + carry) != 0;
         for (int i = 0; i < 8; ++i) r48[i] = ge ? t[i] : out[i];
     }
+    // operand scanning: all 64 products of a * b first (independent of the reduction), then eight reduction rows, each
+    // adding m_k * q to the columns above it; only m_k and the carry stay on the critical path
+    void mul_rows(const u64 *a48, const u64 *b48, u64 *r48) const {
+        double a[8], b[8];
+        for (int i = 0; i < 8; ++i) { a[i] = (double)a48[i]; b[i] = (double)b48[i]; }
+        u64 hi[16] = {0}, lo[16] = {0};
+        int cnt[16] = {0};
+        for (int i = 0; i < 8; ++i)
+            for (int j = 0; j < 8; ++j) { product(a[i], b[j], hi[i + j], lo[i + j]); ++cnt[i + j]; }
+        u64 carry = 0, out[8];
+        for (int k = 0; k < 16; ++k) {
+            u64 col = (lo[k] - (u64)cnt[k] * k_lo) + (k ? hi[k - 1] - (u64)cnt[k - 1] * k_hi : 0) + carry;
+            if (k < 8) {
+                u64 mk = ((col & MASK48) * ninv) & MASK48;
+                double m = (double)mk;
+                for (int j = 0; j < 8; ++j) { product(m, q[j], hi[k + j], lo[k + j]); ++cnt[k + j]; }
+                // the j = 0 product landed in this column after `col` was formed: add its low part
+                u64 h0 = 0, l0 = 0;
+                product(m, q[0], h0, l0);
+                col += l0 - k_lo;
+            } else {
+                out[k - 8] = col & MASK48;
+            }
+            carry = col >> 48;
+        }
+        u64 top = (hi[15] - (u64)cnt[15] * k_hi) + carry;
+        u64 qq[8], t[8];
+        for (int i = 0; i < 8; ++i) qq[i] = (u64)q[i];
+        long long borrow = 0;
+        for (int i = 0; i < 8; ++i) {
+            long long d = (long long)out[i] - (long long)qq[i] - borrow;
+            borrow = d < 0;
+            t[i] = (u64)(d + (borrow ? (long long)(1ull << 48) : 0)) & MASK48;
+        }
+        bool ge = !borrow || top != 0;
+        for (int i = 0; i < 8; ++i) r48[i] = ge ? t[i] : out[i];
+    }
 };
 
 int main() {
@@ -141,6 +178,9 @@ int main() {
         to48(x.l, a48); to48(y.l, b48);
         dpf.mul(a48, b48, r48);
         Fq got;
+        from48(r48, got.l);
+        if (!(got == want)) ++bad;
+        dpf.mul_rows(a48, b48, r48);
         from48(r48, got.l);
         if (!(got == want)) ++bad;
     }
