@@ -23,6 +23,9 @@
  * available from g16_last_error().  There is no CPU fallback: without a CUDA device every
  * compute entry point fails with G16_ERR_NO_DEVICE.  A ctx may be used by one thread at a time.
  * Caller owns all input/output buffers; handles are owned by the library until *_free/_destroy.
+ * Lifetime: g16_bases, g16_pk and g16_r1cs handles belong to the context they were created with and must not be
+ * USED after g16_ctx_destroy; freeing them afterwards is allowed (they release their own device memory and do not
+ * reach through the context), freeing them first is the normal order.
  */
 #ifndef G16_CUDA_H
 #define G16_CUDA_H
@@ -56,10 +59,11 @@ int g16_ctx_set_stream(g16_ctx *ctx, void *cuda_stream);
 int g16_ctx_synchronize(g16_ctx *ctx);
 /* tuning: window bits for the next MSMs (0 = choose from n) */
 int g16_ctx_set_window_bits(g16_ctx *ctx, unsigned c);
-/* tuning: bucket sums as trees of affine additions with block-shared inversions (6 instead of 10 field
- * multiplications per addition) for `rounds` pairwise rounds before the XYZZ tail; 0 or -1 = XYZZ walk only (the
- * default: measured faster on B200).  Process-wide.  Results are unchanged. */
-int g16_ctx_set_affine_rounds(g16_ctx *ctx, int rounds);
+/* tuning: host-scalar MSMs (g16_*_msm, g16_*_msm_oneshot, g16_*_msm_async) of at least min_scalars scalars per
+ * device copy their scalars in three index ranges on a second stream; every range is sorted and accumulated into
+ * the same bucket array as soon as it has arrived, so only the first small copy is exposed.  0 restores the default
+ * (2^19).  Results are unchanged. */
+int g16_ctx_set_h2d_pipeline_min(g16_ctx *ctx, size_t min_scalars);
 int g16_device_count(void);
 const char *g16_version(void);
 
@@ -175,8 +179,10 @@ int g16_quotient_h(g16_ctx *ctx, const uint64_t *a_evals, const uint64_t *b_eval
  *   g16_prove_r1cs          `Prover::prove` (crates/groth16-core/src/lib.rs:139-272) from the un-truncated witness:
  *                           Witness::validate, quotient polynomial, truncations, the five MSMs
  * A matrix is CSR over the constraints: row_ptr[num_constraints + 1], col[nnz] (variable indices; entries with
- * col >= num_variables are ignored like qap/src/lib.rs:121-138 does), val[nnz x 4 u64] (Fr, Montgomery).  A
- * (row, variable) pair may appear at most once per matrix.  Single-device contexts only. */
+ * col >= num_variables are ignored like qap/src/lib.rs:121-138 does), val[nnz x 4 u64] (Fr, Montgomery).  When a
+ * (row, variable) pair appears more than once in a matrix the last value wins, as in the reference's
+ * `a_evals[row][var] = coeff` loop (its linear combinations are maps, so it never sees duplicates).
+ * Single-device contexts only. */
 typedef struct g16_r1cs g16_r1cs;
 typedef struct g16_csr {
     const uint32_t *row_ptr;
@@ -250,13 +256,8 @@ unsigned long long g16_launch_count(void);
  * [digit count, offset scan, scatter, bucket accumulate, bucket reduce, window combine];
  * plan = {window bits, windows, buckets per window} */
 int g16_ctx_enable_stage_timing(g16_ctx *ctx, int on);
-/* host-scalar MSMs with at least min_scalars scalars per device are cut into 4 index ranges that run on
- * separate lanes so the H2D copy of one overlaps the pipeline of another.  Off by default: every chunk pays
- * its own bucket reduction, which costs more than the copy it hides (measured, profiles/README.md). */
-int g16_ctx_set_chunk_min(g16_ctx *ctx, size_t min_scalars);
 int g16_ctx_last_stage_ms(g16_ctx *ctx, float ms[6], unsigned plan[3]);
-/* element-wise Fq ops on the device: op 0 mul, 1 add, 2 sub, 3 inverse(a), 4 square(a), 5 negate(a),
- * 6 square(a) by the dedicated squaring routine (kept for scheduling experiments, see csrc/fp.cuh);
+/* element-wise Fq ops on the device: op 0 mul, 1 add, 2 sub, 3 inverse(a), 4 square(a), 5 negate(a);
  * a, b, out: n x 6 u64 Montgomery (b may be NULL for unary ops) */
 int g16_debug_fq_op(g16_ctx *ctx, int op, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n);
 /* Fr Montgomery -> canonical (`into_bigint()`), n x 4 u64 */

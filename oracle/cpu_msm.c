@@ -136,6 +136,31 @@ void ora_fr_from_mont(const uint64_t *a, uint64_t *r, size_t n) {
 void ora_fr_to_mont(const uint64_t *a, uint64_t *r, size_t n) {
     for (size_t i = 0; i < n; ++i) fr_to_mont(r + 4 * i, a + 4 * i);
 }
+/* sum_i a_i * b_i mod r, all values Fr in Montgomery form (the "discrete-log" side of the exact
+ * large-size checks: with bases P_i = k_i G, sum s_i P_i = (sum s_i k_i) G).  Result in Montgomery form. */
+void ora_dot_mod_r(const uint64_t *a_mont, const uint64_t *b_mont, size_t n, int threads, uint64_t out_mont[4]) {
+    if (threads < 1) threads = 1;
+    uint64_t *part = (uint64_t *)calloc((size_t)threads * 4, 8);
+    _Pragma("omp parallel num_threads(threads) if (threads > 1)")
+    {
+#ifdef _OPENMP
+        int t = omp_get_thread_num(), nt = omp_get_num_threads();
+#else
+        int t = 0, nt = 1;
+#endif
+        uint64_t acc[4] = {0, 0, 0, 0}, prod[4];
+        size_t lo = n * (size_t)t / (size_t)nt, hi = n * ((size_t)t + 1) / (size_t)nt;
+        for (size_t i = lo; i < hi; ++i) {
+            mont_mul(prod, a_mont + 4 * i, b_mont + 4 * i, FR_P, FR_NINV, 4);
+            mod_add(acc, acc, prod, FR_P, 4);
+        }
+        memcpy(part + 4 * t, acc, 32);
+    }
+    uint64_t acc[4] = {0, 0, 0, 0};
+    for (int t = 0; t < threads; ++t) mod_add(acc, acc, part + 4 * t, FR_P, 4);
+    memcpy(out_mont, acc, 32);
+    free(part);
+}
 int ora_msm_window(size_t n) { return n < 32 ? 3 : (int)ln_without_floats(n) + 2; }
 void ora_make_digits(const uint64_t a[4], int w, int64_t *digits) { make_digits(digits, a, w, 255); }
 int ora_max_threads(void) {

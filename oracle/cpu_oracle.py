@@ -48,7 +48,14 @@ def _p8(a):
 
 
 def max_threads() -> int:
-    return lib().ora_max_threads()
+    """Host threads the CPU arm may use: the CPUs this process is allowed to run on.  Deliberately NOT
+    omp_get_max_threads(): launchers such as torch.distributed.run export OMP_NUM_THREADS=1, which made
+    the baseline depend on how bench.py was started.  Every caller passes the count
+    explicitly (num_threads clause), so the environment variable has no effect."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:  # pragma: no cover
+        return max(1, os.cpu_count() or 1)
 
 
 def _msm(name, width, bases, inf, scalars, threads):
@@ -143,6 +150,16 @@ def fr_to_mont(a):
     r = np.zeros_like(a)
     lib().ora_fr_to_mont(_p64(a), _p64(r), ctypes.c_size_t(a.shape[0]))
     return r
+
+
+def dot_mod_r(a_mont, b_mont, threads: int = 0):
+    """sum a_i b_i mod r of two Montgomery Fr vectors; returns the sum in Montgomery form (4 x uint64)."""
+    a = np.ascontiguousarray(a_mont, dtype=np.uint64).reshape(-1, 4)
+    b = np.ascontiguousarray(b_mont, dtype=np.uint64).reshape(-1, 4)
+    assert a.shape == b.shape
+    out = np.zeros(4, dtype=np.uint64)
+    lib().ora_dot_mod_r(_p64(a), _p64(b), ctypes.c_size_t(a.shape[0]), ctypes.c_int(threads or max_threads()), _p64(out))
+    return out
 
 
 def gen_scalars(seed: int, n: int, bits: int = 255):

@@ -133,8 +133,6 @@ def check_debug_field(ctx, oracle, n=2000):
         assert (out == ref(a, b)).all(), op
     assert lib.g16_debug_fq_op(ctx.handle, 4, a.ctypes.data, None, out.ctypes.data, a.shape[0]) == 0
     assert (out == oracle.fq_mul(a, a)).all()
-    assert lib.g16_debug_fq_op(ctx.handle, 6, a.ctypes.data, None, out.ctypes.data, a.shape[0]) == 0   # dedicated squaring
-    assert (out == oracle.fq_mul(a, a)).all()
     assert lib.g16_debug_fq_op(ctx.handle, 5, a.ctypes.data, None, out.ctypes.data, a.shape[0]) == 0
     assert (out == oracle.fq_sub(np.zeros_like(a), a)).all()
     nz = a[a.any(axis=1)][:64]
@@ -178,12 +176,11 @@ def check_debug_group_add(ctx, oracle, gens):
 
 
 def check_chunked_host_path(ctx, oracle, gens, n, seed):
-    """Host-scalar MSMs above the chunk threshold are cut into 4 index ranges that run on separate lanes
-    (H2D of chunk k+1 overlaps the pipeline of chunk k) and are folded on the device: same group element,
-    for plain and for precomputed resident bases, G1 and G2, including a prefix of the bases."""
-    import ctypes
-    ctx.lib.g16_ctx_set_chunk_min.argtypes = [ctypes.c_void_p, ctypes.c_size_t]
-    assert ctx.lib.g16_ctx_set_chunk_min(ctx.handle, 64) == 0
+    """Host-scalar MSMs above the pipeline threshold copy their scalars in three index ranges; every range is sorted
+    and accumulated INTO THE SAME bucket array, which is reduced once (engine.cuh, H2D_PIPE_PARTS): same group
+    element, for plain and for precomputed resident bases, G1 and G2, including a prefix of the bases, infinities,
+    duplicates and skewed scalars whose buckets are split into slices (the add-to path of the slice merge)."""
+    ctx.set_h2d_pipeline_min(64)
     try:
         for group, m in (("g1", n), ("g2", max(70, n // 4))):
             pts, inf, sc = helpers.adversarial(oracle, gens, group, seed, m)
@@ -201,5 +198,7 @@ def check_chunked_host_path(ctx, oracle, gens, n, seed):
             out, oinf = f(bases, sc[:k])
             assert oinf == einf and (out == exp).all(), (group, "prefix")
             bases.free()
+        check_skewed_scalars(ctx, oracle, gens, max(200, n // 2), seed + 3)
+        check_skewed_scalars(ctx, oracle, gens, 1500, seed + 4)      # > ITEM_MAX entries per bucket in every range
     finally:
-        ctx.lib.g16_ctx_set_chunk_min(ctx.handle, 1 << 62)   # back to the default: off
+        ctx.set_h2d_pipeline_min(0)   # back to the default

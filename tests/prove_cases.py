@@ -5,6 +5,7 @@ import numpy as np
 
 import bls12_381 as bls
 import groth16_ref as ref
+import prove_model as pm
 
 
 def pk_to_arrays(pk):
@@ -104,3 +105,49 @@ def check_random_key(ctx, ctx_single, oracle, gens, n, seed, num_public=2):
     for got, exp in ((proofs[0], proofs[2]), (proofs[1], proofs[3])):
         for (gx, gi), (ex, ei) in zip(got, exp):
             assert gi == ei and (gx == ex).all()
+    # ... and both equal the reference's own five MSMs (lib.rs:179,197,220,255,264) on the CPU (C port of ark's Pippenger)
+    assert pm.proofs_equal(proofs[2], pm.five_msms_cpu(pk, w, h, r, s)), "one-device proof differs from the CPU five-MSM model"
+    assert pm.proofs_equal(proofs[3], pm.five_msms_cpu(pk, w, None, r, s)), "proof without H differs from the CPU model"
+
+
+def synthetic_key(ctx, oracle, gens, n, seed, num_public=1, bits=255):
+    """ProvingKey-shaped host arrays k_i * G (built by the engine's fixed-base kernels, spot-checked against the
+    oracle) together with their exponents."""
+    k = pm.synthetic_key_exponents(n, seed, num_public, bits)
+    pk = {"num_public": num_public}
+    for name in ("a_g1", "b_g1", "ic_g1", "h_g1"):
+        pk[name], pk[name + "_inf"] = ctx.fixed_base_mul_g1(gens[0], k[name])
+    pk["b_g2"], pk["b_g2_inf"] = ctx.fixed_base_mul_g2(gens[1], k["b_g2"])
+    for name in ("alpha_g1", "beta_g1", "delta_g1"):
+        pk[name] = oracle.g1_fixed_base_mul(gens[0], k[name][None])[0][0]
+    for name in ("beta_g2", "delta_g2"):
+        pk[name] = oracle.g2_fixed_base_mul(gens[1], k[name][None])[0][0]
+    idx = [0, 1, n // 3, n - num_public - 2]
+    for name in ("a_g1", "ic_g1", "h_g1"):
+        exp, einf = oracle.g1_fixed_base_mul(gens[0], k[name][idx])
+        assert (pk[name][idx] == exp).all() and (pk[name + "_inf"][idx] == einf).all(), name
+    exp, einf = oracle.g2_fixed_base_mul(gens[1], k["b_g2"][idx])
+    assert (pk["b_g2"][idx] == exp).all()
+    return pk, k
+
+
+def check_prove_in_exponent(ctx, oracle, gens, log_n, seed, precompute, bits_list=(255, 64), cpu_msms=False):
+    """BASELINE config 3 / 5 shape: N = n = 2^log_n variables and H coefficients, one public input.  The proof of the
+    engine's schedule (g16_prove) must equal the exact computation in the exponent; with cpu_msms also the five MSMs of
+    the CPU model (sizes the C port finishes in seconds)."""
+    n = 1 << log_n
+    pk, k = synthetic_key(ctx, oracle, gens, n, seed)
+    dev_pk = ctx.pk_upload(pk)
+    if precompute:
+        ctx.pk_precompute(dev_pk)
+    r, s = oracle.gen_scalars(seed + 0xaa, 2)
+    for bits in bits_list:          # full width, and what the reference's 64-bit truncation produces
+        w = oracle.gen_scalars(seed + 0x1000 + bits, n, bits)
+        w[0] = pm.ONE
+        w[7] = 0
+        h = oracle.gen_scalars(seed + 0x2000 + bits, n - 1, bits)
+        got = ctx.prove(dev_pk, w, h, r, s)
+        assert pm.proofs_equal(got, pm.proof_in_exponent(k, 1, w, h, r, s, gens)), f"2^{log_n} proof, {bits}-bit scalars"
+        if cpu_msms:
+            assert pm.proofs_equal(got, pm.five_msms_cpu(pk, w, h, r, s))
+    dev_pk.free()

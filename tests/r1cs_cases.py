@@ -107,6 +107,35 @@ def check_evals_small(ctx):
         dev.free()
 
 
+def check_duplicate_entries(ctx):
+    """A (row, variable) pair given twice in the CSR input: the LAST coefficient wins, as in the assignment loop of
+    QAP::from_r1cs (`a_evals[row][var] = coeff`, qap/src/lib.rs:121-138) -- not the sum.  Columns >= num_variables
+    are ignored."""
+    constraints, nvars, w, _ = chain_circuit(0xd0, 6)
+    clean = [to_csr(constraints, k) for k in range(3)]
+    dirty = []
+    for k in range(3):
+        row_ptr, col, val = [0], [], []
+        for i, row in enumerate(constraints):
+            items = sorted(row[k].items())
+            v0, c0 = items[0]
+            col += [v0, nvars + 5]                       # a stale coefficient first, and an out-of-range column
+            val += [(c0 + 12345 + i) % R, 777]
+            for v, coef in items[1:]:
+                col.append(v); val.append(coef % R)
+            col.append(v0); val.append(c0 % R)           # the value that must survive
+            row_ptr.append(len(col))
+        dirty.append((np.array(row_ptr, dtype=np.uint32), np.array(col, dtype=np.uint32), fr_arr(val)))
+    d_clean = ctx.r1cs_upload(len(constraints), nvars, *clean)
+    d_dirty = ctx.r1cs_upload(len(constraints), nvars, *dirty)
+    for a, b in zip(ctx.r1cs_domain_evals(d_clean, fr_arr(w)), ctx.r1cs_domain_evals(d_dirty, fr_arr(w))):
+        assert (a == b).all()
+    s = fr_arr([ref.P_RAND["s"]])[0]
+    for a, b in zip(ctx.r1cs_eval_at(d_clean, s), ctx.r1cs_eval_at(d_dirty, s)):
+        assert (a == b).all()
+    d_clean.free(); d_dirty.free()
+
+
 def check_evals_long_lines(ctx, m=700):
     """> 256 entries in one line (the constant column, one wide row): block-summed lines; ignored out-of-range columns."""
     constraints, nvars, w, npub = chain_circuit(0xc3, m, bits=64)

@@ -51,6 +51,7 @@ def test_emu_quotient_polynomial(emu_ctx):
 def test_emu_r1cs_evaluations(emu_ctx):
     import r1cs_cases as rc
     rc.check_evals_small(emu_ctx)
+    rc.check_duplicate_entries(emu_ctx)
     rc.check_evals_long_lines(emu_ctx, m=300)
 
 
@@ -58,21 +59,6 @@ def test_emu_r1cs_setup_and_prove(emu_ctx):
     import r1cs_cases as rc
     rc.check_setup_and_prove(emu_ctx, circuits=rc.CIRCUITS[:3])
     rc.check_errors(emu_ctx)
-
-
-def test_emu_affine_bucket_accumulation(emu_ctx, oracle, gens):
-    """affine_acc.cuh (serial statement of the schedule): pair classification, slot layout, tail."""
-    for rounds in (1, 3, 8):
-        emu_ctx.set_affine_rounds(rounds)
-        try:
-            pc.check_golden_msm(emu_ctx)
-            pc.check_random_msm(emu_ctx, oracle, gens, "g1", 257, 1, windows=(0, 3, 7), pre=(8,))
-            pc.check_random_msm(emu_ctx, oracle, gens, "g2", 40, 2, windows=(5,), pre=(9,))
-            pc.check_adversarial(emu_ctx, oracle, gens, "g1", 300, 5)
-            pc.check_adversarial(emu_ctx, oracle, gens, "g2", 60, 6)
-            pc.check_skewed_scalars(emu_ctx, oracle, gens, 1500, 8)
-        finally:
-            emu_ctx.set_affine_rounds(-1)
 
 
 def test_emu_wire_format(emu_ctx):

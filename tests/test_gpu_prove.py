@@ -33,6 +33,7 @@ def test_quotient_polynomial_ntt(gpu_ctx):
 def test_r1cs_evaluations(gpu_ctx):
     import r1cs_cases as rc
     rc.check_evals_small(gpu_ctx)
+    rc.check_duplicate_entries(gpu_ctx)
     rc.check_evals_long_lines(gpu_ctx, m=700)
 
 
@@ -61,3 +62,26 @@ def test_prove_multi_device_random_key(gpu_ctx, oracle, gens):
             prove_cases.check_random_key(ctx, gpu_ctx, oracle, gens, n=3001, seed=len(devs))
         finally:
             ctx.close()
+
+
+def test_prove_matches_cpu_five_msms_and_exponent_2_13(gpu_ctx, oracle, gens):
+    """The prove schedule against BOTH checkers at a size the CPU model finishes in seconds."""
+    prove_cases.check_prove_in_exponent(gpu_ctx, oracle, gens, 13, 0x13000, precompute=False, cpu_msms=True)
+    prove_cases.check_prove_in_exponent(gpu_ctx, oracle, gens, 13, 0x13100, precompute=True, bits_list=(255,), cpu_msms=True)
+
+
+def test_prove_config3_2_20_in_exponent(gpu_ctx, oracle, gens):
+    """BASELINE config 3 at full size (2^20 variables / H coefficients, resident precomputed key): g16_prove checked
+    exactly in the exponent -- every base is k_i * G with known k_i (crates/groth16-core/src/lib.rs:164-271)."""
+    prove_cases.check_prove_in_exponent(gpu_ctx, oracle, gens, 20, 0x20000, precompute=True)
+
+
+def test_prove_config3_2_20_multi_shard_in_exponent(oracle, gens):
+    """The same on a sharded context (all GPUs of the box, or three index-range shards on one GPU)."""
+    import groth16_cuda
+    ndev = groth16_cuda.load_library().g16_device_count()
+    ctx = groth16_cuda.Context(devices=list(range(min(ndev, 8))) if ndev > 1 else [0, 0, 0])
+    try:
+        prove_cases.check_prove_in_exponent(ctx, oracle, gens, 20, 0x20300, precompute=False, bits_list=(255,))
+    finally:
+        ctx.close()

@@ -11,6 +11,7 @@ from __future__ import annotations
 import argparse
 import concurrent.futures as cf
 import glob
+import hashlib
 import os
 import subprocess
 import sys
@@ -28,6 +29,18 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 
 
+def source_hash() -> str:
+    """sha256 over csrc/*.cu, csrc/*.cuh and include/*.h (names + contents, sorted): baked into g16_version()."""
+    h = hashlib.sha256()
+    files = sorted(glob.glob(os.path.join(CSRC, "*.cu")) + glob.glob(os.path.join(CSRC, "*.cuh")) +
+                   glob.glob(os.path.join(INCLUDE, "*.h")))
+    for f in files:
+        h.update(os.path.basename(f).encode() + b"\0")
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
 def _newest_header() -> float:
     hdrs = glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(INCLUDE, "*.h"))
     return max(os.path.getmtime(h) for h in hdrs)
@@ -37,10 +50,19 @@ def _compile(unit: str, force: bool, verbose: bool):
     src = os.path.join(CSRC, unit)
     obj = os.path.join(OBJDIR, unit.replace(".cu", ".o"))
     log = obj + ".log"
-    if not force and os.path.exists(obj) and os.path.getmtime(obj) >= max(os.path.getmtime(src), _newest_header()):
+    digest = source_hash()
+    stamp = obj + ".hash"
+    if unit == "version.cu":
+        # cheap and always exact: rebuilt whenever any source changed since the last build
+        fresh = os.path.exists(obj) and os.path.exists(stamp) and open(stamp).read() == digest
+        if not force and fresh:
+            return unit, 0.0, "cached"
+    elif not force and os.path.exists(obj) and os.path.getmtime(obj) >= max(os.path.getmtime(src), _newest_header()):
         return unit, 0.0, "cached"
     t0 = time.time()
     cmd = [NVCC] + ARCH + COMMON + ["-c", src, "-o", obj]
+    if unit == "version.cu":
+        cmd += [f'-DG16_SOURCE_HASH="{digest}"']
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     with open(log, "w") as f:
         f.write(res.stdout)
@@ -48,6 +70,9 @@ def _compile(unit: str, force: bool, verbose: bool):
         raise RuntimeError(f"nvcc failed for {unit}:\n{res.stdout[-4000:]}")
     if verbose:
         print(res.stdout)
+    if unit == "version.cu":
+        with open(stamp, "w") as f:
+            f.write(digest)
     return unit, time.time() - t0, "built"
 
 

@@ -5,8 +5,6 @@
 
 extern "C" {
 
-const char *g16_version(void) { return "groth16-cuda 0.1 (sm_100a)"; }
-
 int g16_device_count(void) {
 #ifndef G16_EMU
     int n = 0;
@@ -46,9 +44,9 @@ int g16_ctx_create(const int *devices, int ndev, g16_ctx **out) {
             d.id = id;
 #ifndef G16_EMU
             G16_CUDA_CHECK(cudaSetDevice(id));
-            // The point gathers of the bucket kernels touch 96-byte records at random; the default L2 fetch
-            // granularity pulls whole 128-byte lines from DRAM (measured: 200 B per 96-byte point).  A hint, per device.
-            if (const char *g = getenv("G16_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g));
+            int sms = 0;
+            G16_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, id));
+            d.sm_count = (uint32_t)std::max(1, sms);
             G16_CUDA_CHECK(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
             d.own_stream = true;
 #endif
@@ -117,9 +115,9 @@ int g16_ctx_set_window_bits(g16_ctx *ctx, unsigned c) {
     return G16_OK;
 }
 
-int g16_ctx_set_affine_rounds(g16_ctx *ctx, int rounds) {
-    if (!ctx || rounds < -1 || rounds > (int)AFF_MAX_ROUNDS_API) return G16_ERR_INVALID;
-    affine_rounds_setting() = rounds;
+int g16_ctx_set_h2d_pipeline_min(g16_ctx *ctx, size_t min_scalars) {
+    if (!ctx) return G16_ERR_INVALID;
+    ctx->c.h2d_pipe_min = min_scalars ? min_scalars : H2D_PIPE_MIN;
     return G16_OK;
 }
 
@@ -156,7 +154,7 @@ static int bases_from_device_impl(g16_ctx *ctx, const void *dev_xy, size_t n, g1
         h->b.reset(new Bases);
         h->b->ctx = &ctx->c; h->b->group = GroupOf<F>::id; h->b->n = n;
         BasesShard sh;
-        sh.dev = 0; sh.pts = (uint32_t *)dev_xy; sh.begin = 0; sh.n = n; sh.owned = false;
+        sh.dev = 0; sh.cuda_dev = ctx->c.devs[0].id; sh.pts = (uint32_t *)dev_xy; sh.begin = 0; sh.n = n; sh.owned = false;
         h->b->shards.push_back(sh);
         *out = h.release();
     });
@@ -458,7 +456,7 @@ void prove_single_device(Context *c, const g16_pk *pk, const uint64_t *w, size_t
     copy_d2d(d_adhoc_pts + 24, oa, 96, LC.stream);
     copy_d2d(d_adhoc_pts + 48, ob1, 96, LC.stream);
     BasesShard adhoc;
-    adhoc.dev = 0; adhoc.pts = d_adhoc_pts; adhoc.n = 3; adhoc.owned = false;
+    adhoc.dev = 0; adhoc.cuda_dev = d0.id; adhoc.pts = d_adhoc_pts; adhoc.n = 3; adhoc.owned = false;
     msm_run<Fq>(LC, adhoc, d_small + 5 * 8, 3, true, 0, d_cparts + PW1, nullptr);
     k_partial_combine<Fq>(LC.stream, d_cparts, 2, nullptr, d_c_aff);
 
@@ -584,7 +582,7 @@ void prove_multi_device(Context *c, const g16_pk *pk, const uint64_t *w, size_t 
     copy_d2d(d_adhoc_pts + 48, ob1, 96, LC0.stream);
     for (size_t k = 1; k < G; ++k) copy_d2d(part_of(4, 0) + k * PW1, part_of(4, k), PW1 * 4, LC0.stream);
     BasesShard adhoc;
-    adhoc.dev = 0; adhoc.pts = d_adhoc_pts; adhoc.n = 3; adhoc.owned = false;
+    adhoc.dev = 0; adhoc.cuda_dev = d0.id; adhoc.pts = d_adhoc_pts; adhoc.n = 3; adhoc.owned = false;
     const uint32_t *d_small0 = (const uint32_t *)lane_of(d0, 0).ws.prove_misc.p;
     msm_run<Fq>(LC0, adhoc, d_small0 + 5 * 8, 3, true, 0, part_of(4, 0) + G * PW1, nullptr);
     uint32_t *d_c_aff = d_adhoc_pts + 3 * 24;
@@ -643,11 +641,6 @@ int g16_quotient_h(g16_ctx *ctx, const uint64_t *a_evals, const uint64_t *b_eval
 // ---- test hooks --------------------------------------------------------------------------------
 unsigned long long g16_launch_count(void) { return launch_count(); }
 
-int g16_ctx_set_chunk_min(g16_ctx *ctx, size_t min_scalars) {
-    if (!ctx || min_scalars < 8) return G16_ERR_INVALID;
-    ctx->c.chunk_min = min_scalars;
-    return G16_OK;
-}
 int g16_ctx_enable_stage_timing(g16_ctx *ctx, int on) {
     if (!ctx) return G16_ERR_INVALID;
     for (auto &d : ctx->c.devs) { d.timer.enabled = on != 0; d.timer.valid = false; }

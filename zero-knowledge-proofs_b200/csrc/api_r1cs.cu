@@ -7,8 +7,26 @@ struct g16_r1cs { std::unique_ptr<R1cs> r; };
 
 namespace {
 
+// Scratch of one setup call.  Everything in it derives from the toxic waste (alpha .. s): the destructor -- reached
+// on success and on every error path alike -- zeroes the buffers before it returns them to the allocator.
 struct SetupWork {
     DevBuf params, blk, lag, vals, ab, ic, h, singles_sc, flags;
+    stream_t st = nullptr;
+    explicit SetupWork(stream_t s) : st(s) {}
+    SetupWork(const SetupWork &) = delete;
+    SetupWork &operator=(const SetupWork &) = delete;
+    ~SetupWork() {
+        DevBuf *all[] = {&params, &blk, &lag, &vals, &ab, &ic, &h, &singles_sc, &flags};
+#ifndef G16_EMU
+        for (DevBuf *b : all)
+            if (b->p) cudaMemsetAsync(b->p, 0, b->cap, st);   // destructors must not throw: unchecked on purpose
+        cudaStreamSynchronize(st);
+#else
+        for (DevBuf *b : all)
+            if (b->p) memset(b->p, 0, b->cap);
+#endif
+        for (DevBuf *b : all) b->release();
+    }
 };
 
 // device array of (prefix + n) packed points owned by a Bases object
@@ -17,7 +35,7 @@ std::unique_ptr<Bases> make_device_bases(Context *c, size_t n_total) {
     std::unique_ptr<Bases> b(new Bases);
     b->ctx = c; b->group = GroupOf<F>::id; b->n = n_total;
     BasesShard sh;
-    sh.dev = 0; sh.begin = 0; sh.n = n_total; sh.owned = true;
+    sh.dev = 0; sh.cuda_dev = c->devs[0].id; sh.begin = 0; sh.n = n_total; sh.owned = true;
     sh.pts = (uint32_t *)dev_alloc(std::max<size_t>(n_total, 1) * 2 * FieldWords<F>::N * 4);
     b->shards.push_back(sh);
     return b;
@@ -88,7 +106,7 @@ int g16_r1cs_eval_at(g16_ctx *ctx, const g16_r1cs *r1cs, const uint64_t s[4], ui
         require(s && a_vals && b_vals && c_vals, "NULL argument");
         const R1cs &r = *r1cs->r;
         size_t n = (size_t)1 << r.log_n;
-        SetupWork w;
+        SetupWork w(dv.stream);
         uint64_t params[20] = {0};
         memcpy(params + 16, s, 32);
         uint32_t *d_params = w.params.as<uint32_t>(40);
@@ -102,7 +120,6 @@ int g16_r1cs_eval_at(g16_ctx *ctx, const g16_r1cs *r1cs, const uint64_t s[4], ui
         copy_d2h(b_vals, vals + r.nv * 8, r.nv * 32, dv.stream);
         copy_d2h(c_vals, vals + 2 * r.nv * 8, r.nv * 32, dv.stream);
         stream_sync(dv.stream);
-        w.params.release(); w.blk.release(); w.lag.release(); w.vals.release();
     });
 }
 
@@ -124,8 +141,7 @@ int g16_setup_crs(g16_ctx *ctx, const g16_r1cs *r1cs, const uint64_t alpha[4], c
             throw Error{G16_ERR_INVALID, "Invalid setup parameters: Number of public inputs must be less than total variables"};
         size_t n = (size_t)1 << r.log_n, nv = r.nv;
         stream_t st = dv.stream;
-        SetupWork w;
-        struct Cleanup { SetupWork &w; ~Cleanup() { w.params.release(); w.blk.release(); w.lag.release(); w.vals.release(); w.ab.release(); w.ic.release(); w.h.release(); w.singles_sc.release(); w.flags.release(); } } cleanup{w};
+        SetupWork w(st);
         uint64_t params[20];
         memcpy(params, alpha, 32); memcpy(params + 4, beta, 32); memcpy(params + 8, gamma, 32); memcpy(params + 12, delta, 32);
         memcpy(params + 16, s, 32);

@@ -18,7 +18,6 @@ struct DebugFqOp {
             case 3: r = Fq::inv(x); break;
             case 4: r = Fq::sqr(x); break;
             case 5: r = Fq::neg(x); break;
-            case 6: r = Fq::sqr_sos(x); break;
             default: r = Fq::zero();
         }
         for (int j = 0; j < 12; ++j) out[12 * i + j] = r.l[j];

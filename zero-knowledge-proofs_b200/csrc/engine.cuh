@@ -13,13 +13,13 @@ enum Group { GROUP_G1 = 1, GROUP_G2 = 2 };
 template <class F> struct GroupOf { static constexpr int id = FieldWords<F>::group; };
 
 struct Workspace {
-    DevBuf scalars, counts, codes, ranks, bins, items, item_start, chunk_out, cursor, entries, buckets, affine, scatter_stage, red[6], scan_tmp, out, partials, staging;
+    DevBuf scalars, counts, codes, ranks, bins, items, item_start, chunk_out, cursor, entries, buckets, scatter_stage, red[6], scan_tmp, out, partials, staging;
     DevBuf prove_w, prove_misc, ntt_abc, ntt_tw, ntt_consts, ntt_out;
     uint32_t ntt_log_n = 0xffffffffu;   // size the cached twiddles / constants were built for (none yet)
     DevBuf fb_base, fb_powers, fb_table[3], fb_out, fb_flags;
     std::vector<uint32_t> fb_table_key[3];  // base limbs the cached table was built for
     void release() {
-        scalars.release(); counts.release(); codes.release(); ranks.release(); bins.release(); items.release(); item_start.release(); chunk_out.release(); cursor.release(); entries.release(); buckets.release(); affine.release(); scatter_stage.release();
+        scalars.release(); counts.release(); codes.release(); ranks.release(); bins.release(); items.release(); item_start.release(); chunk_out.release(); cursor.release(); entries.release(); buckets.release(); scatter_stage.release();
         for (auto &r : red) r.release();
         scan_tmp.release(); out.release(); partials.release(); staging.release();
         prove_w.release(); prove_misc.release(); ntt_abc.release(); ntt_tw.release(); ntt_consts.release(); ntt_out.release(); ntt_log_n = 0xffffffffu; fb_base.release(); fb_powers.release(); fb_out.release(); fb_flags.release();
@@ -70,6 +70,7 @@ struct StageTimer {
 
 struct Device {
     int id = 0;
+    uint32_t sm_count = 1;   // multiprocessors of this GPU (cudaDeviceProp), sizes the grid-stride launches
     stream_t stream = nullptr;
     bool own_stream = false;
     Workspace ws;
@@ -78,7 +79,6 @@ struct Device {
     // extra lanes (own stream + workspace) on the same GPU: lets the latency-bound tail of one MSM
     // (reduction tree, inversion) overlap the bucket accumulation of another (prove schedule)
     std::vector<std::unique_ptr<Device>> extra;
-    std::vector<uint32_t> host_partials;   // per-lane staging for the sharded combine
 };
 
 inline void set_device(int id);
@@ -94,6 +94,7 @@ inline Device &lane_of(Device &dv, int k) {
     while ((int)dv.extra.size() < k) {
         std::unique_ptr<Device> l(new Device);
         l->id = dv.id;
+        l->sm_count = dv.sm_count;
 #ifndef G16_EMU
         G16_CUDA_CHECK(cudaSetDevice(dv.id));
         G16_CUDA_CHECK(cudaStreamCreateWithFlags(&l->stream, cudaStreamNonBlocking));
@@ -112,27 +113,29 @@ inline void set_device(int id) {
 #endif
 }
 
-// host-scalar MSMs of at least H2D_PIPE_MIN scalars copy them in H2D_PIPE_CHUNKS pieces on lane H2D_PIPE_LANE
+// Host-scalar MSMs of at least `h2d_pipe_min` scalars are cut into H2D_PIPE_PARTS index ranges of growing size
+// (1/32, 5/32, 26/32 of the scalars).  The ranges are copied back to back on a second stream; each one is decomposed,
+// sorted and accumulated INTO THE SAME bucket array as soon as it has arrived, and the buckets are reduced once at the
+// end -- so only the first, small copy is exposed (0.3 ms of 9.7 ms at 2^24) and no range pays its own reduction.
 #ifndef G16_EMU
-constexpr size_t H2D_PIPE_MIN = (size_t)1 << 20;
+constexpr size_t H2D_PIPE_MIN = (size_t)1 << 19;
 #else
-constexpr size_t H2D_PIPE_MIN = 64;   // the emulation tests walk the chunk offsets on small inputs
+constexpr size_t H2D_PIPE_MIN = 64;   // the emulation tests walk the chunk logic on small inputs
 #endif
-constexpr size_t H2D_PIPE_CHUNKS = 8;
-constexpr int H2D_PIPE_LANE = 7;   // lanes 0-4: prove schedule, 8+: chunk pipelines
-constexpr size_t CHUNK_MIN_SCALARS = ~(size_t)0;   // chunked host-scalar pipeline: off by default
-constexpr size_t H2D_CHUNKS = 4;
-constexpr int CHUNK_LANE_BASE = 8;                // lanes 8.. are reserved for chunk pipelines
+constexpr size_t H2D_PIPE_PARTS = 3;
+constexpr size_t H2D_PIPE_NUM[H2D_PIPE_PARTS + 1] = {0, 1, 6, 32};   // cumulative 32nds
+constexpr int H2D_PIPE_LANE = 7;   // lanes 0-4: prove schedule
 
 struct Context {
     std::vector<Device> devs;
     std::string err;
     unsigned c_override = 0;
-    size_t chunk_min = CHUNK_MIN_SCALARS;   // host-scalar MSMs at least this long are pipelined in chunks
+    size_t h2d_pipe_min = H2D_PIPE_MIN;
 };
 
 struct BasesShard {
-    int dev = 0;  // index into Context::devs
+    int dev = 0;       // index into Context::devs
+    int cuda_dev = 0;  // CUDA ordinal of that device (the destructor must not reach through the context)
     uint32_t *pts = nullptr;
     size_t begin = 0, n = 0;
     bool owned = true;
@@ -142,7 +145,7 @@ struct BasesShard {
 };
 
 struct Bases {
-    Context *ctx = nullptr;
+    Context *ctx = nullptr;   // identity check + launch-time lookup; never dereferenced by the destructor
     int group = 0;
     size_t n = 0;
     std::vector<BasesShard> shards;
@@ -150,7 +153,7 @@ struct Bases {
         for (auto &s : shards)
         {
             // destructors must not throw: select the device without the checking wrapper
-            if ((s.owned && s.pts) || s.table) set_device_nothrow(ctx->devs[s.dev].id);
+            if ((s.owned && s.pts) || s.table) set_device_nothrow(s.cuda_dev);
             if (s.owned && s.pts) dev_free(s.pts);
             if (s.table) dev_free(s.table);
         }
@@ -216,48 +219,34 @@ inline unsigned choose_precompute_c(size_t n, size_t point_bytes, size_t budget)
     return best_c;
 }
 
-// Affine bucket accumulation (affine_acc.cuh): number of pairwise rounds before the XYZZ tail.  Default 0 = the
-// XYZZ walk.  MEASURED (B200, 2^24, c = 22, profiles/README.md runs 13-14): the tree retires ~28 % fewer integer
-// multiplies and its later rounds run at 0.21 ms per million additions against 0.35 for the XYZZ walk, but round 0
-// has to gather every base point twice (denominators, then the additions) from a 19 GB table at 128-byte DRAM
-// granularity -- 80 GB of traffic, 37 ms for half of the additions -- so the whole accumulation takes 78.7 ms
-// instead of 72.7.  Kept, bit-exact and tested, as an opt-in (g16_ctx_set_affine_rounds / G16_AFFINE_ROUNDS).
-inline int &affine_rounds_setting() {
-    static int v = getenv("G16_AFFINE_ROUNDS") ? atoi(getenv("G16_AFFINE_ROUNDS")) : -1;
-    return v;
-}
-constexpr int AFF_MAX_ROUNDS_API = 8;
-inline uint32_t affine_rounds_for(size_t entries, size_t buckets) {
-    int v = affine_rounds_setting();
-    if (v <= 0) return 0;
-    (void)entries; (void)buckets;
-    return (uint32_t)std::min<int>(v, AFF_MAX_ROUNDS_API);
-}
-
 constexpr size_t SCATTER_TWO_PASS_BYTES = (size_t)96 << 20;   // `entries` larger than this (~L2) are scattered in two passes
 constexpr uint32_t REDUCE_LOG_L = 5;
+// longest work item: 256 additions when the call is large (a serial walk of 256 is noise), shorter when it is small
+// and the longest item would set the kernel's duration: max(ITEM_FLOOR, entries >> ITEM_SHIFT).  Floor 16: at
+// 2^16 / 2^18 pairs the 2^15 buckets alone are too few threads, cutting them into slices of <= 16 / 32 entries takes
+// the accumulation from 0.79 to 0.70 ms and from 2.39 to 2.02 ms (profiles/README.md run 23)
+constexpr size_t ITEM_FLOOR = 16;
+constexpr unsigned ITEM_SHIFT = 17;
 // Levels with at most 2^tile_max_log2 entries run block-cooperatively; a thread level aims to leave 2^groups_log2 groups
 // behind.  Measured on B200 (profiles/README.md run 19): 15 / 15 is best up to 2^20 buckets (reduce 1.14 -> 0.99 ms at 2^19
-// buckets), 17 / 16 beyond (3.07 -> 3.00 ms at 2^21).  G16_REDUCE_GROUPS_LOG2 / G16_TILE_MAX_LOG2 override for tuning runs.
+// buckets), 17 / 16 beyond (3.07 -> 3.00 ms at 2^21).
 inline void reduce_split(size_t buckets, size_t &tile_level_max, size_t &thread_level_groups) {
-    static const int env_g = getenv("G16_REDUCE_GROUPS_LOG2") ? atoi(getenv("G16_REDUCE_GROUPS_LOG2")) : 0;
-    static const int env_t = getenv("G16_TILE_MAX_LOG2") ? atoi(getenv("G16_TILE_MAX_LOG2")) : 0;
     bool big = buckets > ((size_t)1 << 20);
-    thread_level_groups = (size_t)1 << (env_g ? env_g : (big ? 17 : 15));
-    tile_level_max = (size_t)1 << (env_t ? env_t : (big ? 16 : 15));
+    thread_level_groups = (size_t)1 << (big ? 17 : 15);
+    tile_level_max = (size_t)1 << (big ? 16 : 15);
 }
 
 // One MSM on one device, asynchronous on dv.stream.
 //   pts        : packed affine bases on this device (n points)
 //   d_scalars  : n x 8 u32 on this device
 //   d_out_xyzz : 4*FieldWords<F>::N words (may be null), d_out_aff : 2*FieldWords<F>::N + 1 words (may be null)
-// h_scalars (optional): the scalars still live on the host; they are copied into d_stage (= d_scalars) here, in chunks on a
-// second stream, each chunk's digit decomposition starting as soon as it has arrived -- the first stage of the pipeline
-// hides under the H2D copy (1.8 ms of a 9.7 ms copy at 2^24).
+// h_scalars (optional): the scalars still live on the host and are copied into d_scalars here.  From pipe_min scalars
+// on, in H2D_PIPE_PARTS ranges on a second stream, each range going through stages 1-4 into the shared bucket array as
+// soon as it has arrived (see H2D_PIPE_PARTS above); below that, one copy in front of the pipeline.
 template <class F>
 void msm_run(Device &dv, const BasesShard &sh, const uint32_t *d_scalars, size_t n, bool mont, unsigned c_override,
              uint32_t *d_out_xyzz, uint32_t *d_out_aff, size_t first = 0, const uint64_t *h_scalars = nullptr,
-             uint32_t *d_stage = nullptr) {
+             size_t pipe_min = ~(size_t)0) {
     // bases [first, first + n) of the shard
     const uint32_t *pts = sh.table ? sh.table : sh.pts;
     stream_t s = dv.stream;
@@ -268,101 +257,95 @@ void msm_run(Device &dv, const BasesShard &sh, const uint32_t *d_scalars, size_t
     }
     if (n >= (1ull << 31)) throw Error{G16_ERR_INVALID, "MSM length must be < 2^31"};
     MsmPlan plan = sh.table ? make_shared_plan(sh.pre_c, sh.n) : make_plan(n, c_override, 2 * FieldWords<F>::N);
-    plan.offset = (uint32_t)first;
     size_t total = plan.total;
     if ((double)n * plan.nwin >= 4294967295.0) throw Error{G16_ERR_INVALID, "n * windows exceeds 2^32 entries"};
-
+    plan.offset = (uint32_t)first;
     dv.last_plan = plan;
-    size_t max_entries = n * plan.nwin;
-    dv.timer.mark(0, s);
-    // 1. canonical scalars -> signed digits: bucket histogram + per-window code array
-    uint32_t *counts = ws.counts.as<uint32_t>(total + 1);
-    dev_memset(counts, 0, (total + 1) * sizeof(uint32_t), s);
-    uint32_t *codes = ws.codes.as<uint32_t>(max_entries);
-    static const bool ranked = getenv("G16_ATOMIC_SCATTER") == nullptr;   // default: rank-based scatter
-    uint32_t *ranks = ranked ? ws.ranks.as<uint32_t>(max_entries) : nullptr;
-    if (h_scalars && n >= H2D_PIPE_MIN) {
-        Device &cp = lane_of(dv, H2D_PIPE_LANE);
-        stream_wait(cp.stream, s);   // earlier work on s may still read the staging buffer
-        for (size_t k = 0; k < H2D_PIPE_CHUNKS; ++k) {
-            size_t lo = n * k / H2D_PIPE_CHUNKS, hi = n * (k + 1) / H2D_PIPE_CHUNKS;
-            if (hi == lo) continue;
-            copy_h2d(d_stage + lo * 8, h_scalars + lo * 4, (hi - lo) * 32, cp.stream);
-            stream_wait(s, cp.stream);
-            k_digit_decompose(s, n, d_scalars, mont, plan, counts, codes, ranks, lo, hi - lo);
-        }
-    } else {
-        if (h_scalars) copy_h2d(d_stage, h_scalars, n * 32, s);
-        k_digit_decompose(s, n, d_scalars, mont, plan, counts, codes, ranks);
+
+    // index ranges of the scalars that run stages 1-4 one after the other (one range unless the H2D copy is pipelined)
+    size_t part_lo[H2D_PIPE_PARTS + 1] = {0, n, n, n}, parts = 1;
+    if (h_scalars && n >= pipe_min && n >= 64) {
+        parts = H2D_PIPE_PARTS;
+        for (size_t k = 1; k < parts; ++k) part_lo[k] = n * H2D_PIPE_NUM[k] / H2D_PIPE_NUM[parts];
+        part_lo[parts] = n;
     }
-    dv.timer.mark(1, s);
-    // 2. bucket offsets (exclusive scan; offsets[total] = number of entries) and the work-item list
-    //    (bucket slices ordered by length, longest first)
+    size_t n_max = 0;
+    for (size_t k = 0; k < parts; ++k) n_max = std::max(n_max, part_lo[k + 1] - part_lo[k]);
+
+    // workspaces sized for the largest range, taken before anything is queued (growing a buffer frees the old one)
+    const size_t max_entries = n_max * plan.nwin;
+    const size_t nbins = k_item_bins();
+    uint32_t *counts = ws.counts.as<uint32_t>(total + 1);
+    uint32_t *codes = ws.codes.as<uint32_t>(max_entries);
+    uint32_t *ranks = ws.ranks.as<uint32_t>(max_entries);
     uint32_t *scan_tmp = ws.scan_tmp.as<uint32_t>(k_scan_tmp_words(total + 1));
-    k_exclusive_scan(s, counts, counts, total + 1, scan_tmp);
-    uint32_t *offsets = counts;
-    size_t nbins = k_item_bins();
-    // longest work item: 256 additions when the call is large (a serial walk of 256 is noise), shorter
-    // when it is small and the longest item would set the kernel's duration.  Floor 16 (was 64): at 2^16 / 2^18 pairs the
-    // 2^15 buckets alone are too few threads, cutting them into chunks of <= 16 / 32 entries takes the accumulation from
-    // 0.79 to 0.70 ms and from 2.39 to 2.02 ms (profiles/README.md run 23); G16_ITEM_FLOOR / G16_ITEM_SHIFT for tuning runs
-    static const size_t item_floor = getenv("G16_ITEM_FLOOR") ? (size_t)atoi(getenv("G16_ITEM_FLOOR")) : 16;
-    static const unsigned item_shift = getenv("G16_ITEM_SHIFT") ? (unsigned)atoi(getenv("G16_ITEM_SHIFT")) : 17;
-    uint32_t item_max = (uint32_t)std::min<size_t>(k_item_max(), std::max<size_t>(item_floor, max_entries >> item_shift));
     uint32_t *bins = ws.bins.as<uint32_t>(2 * (nbins + 1));
     uint32_t *bin_cursor = bins + nbins + 1;
-    dev_memset(bins, 0, (nbins + 1) * sizeof(uint32_t), s);
-    k_item_count(s, total, offsets, item_max, bins);
-    k_exclusive_scan(s, bins, bins, nbins + 1, scan_tmp);
-    copy_d2d(bin_cursor, bins, (nbins + 1) * sizeof(uint32_t), s);
-    size_t max_split_buckets = max_entries / item_max + 1;           // buckets longer than item_max
-    size_t max_split = 2 * max_split_buckets + 16;                   // chunks they are cut into
-    size_t max_items = total + max_split;
+    const size_t item_min = std::min<size_t>(k_item_max(), ITEM_FLOOR);
+    const size_t max_split_buckets = max_entries / item_min + 1;     // buckets longer than the shortest item limit
+    const size_t max_split = 2 * max_split_buckets + 16;             // chunks they are cut into
+    const size_t max_items = total + max_split;
     WorkItem *items = (WorkItem *)ws.items.need(max_items * k_item_bytes());
     uint32_t *split_list = ws.item_start.as<uint32_t>(1 + 3 * max_split_buckets);
-    dev_memset(split_list, 0, sizeof(uint32_t), s);
-    k_item_scatter(s, total, offsets, item_max, bin_cursor, items, split_list);
-    dv.timer.mark(2, s);
-    // 3. counting-sort scatter of (point index, sign) into bucket order, one window at a time
     uint32_t *entries = ws.entries.as<uint32_t>(max_entries);
-    if (ranked) {
-        // shared bucket set (precomputed bases): a window's writes spread over the whole entries array, so
-        // sweep the bucket range in slabs of <= ~48 MB of entries; per-window bucket sets are local already
-        static const size_t slab_bytes = getenv("G16_SCATTER_SLAB_MB") ? (size_t)atol(getenv("G16_SCATTER_SLAB_MB")) << 20 : (size_t)0;   // off: measured slower (one thread per code per slab)
-        size_t slabs = (plan.bwin == 1 && slab_bytes) ? (max_entries * 4 + slab_bytes - 1) / slab_bytes : 1;
-        if (slabs > 64) slabs = 64;
-        // entry arrays beyond L2 go through the two-pass partitioned scatter (msm_kernels.cuh); G16_SCATTER_ONE_PASS
-        // keeps the one-pass kernel for comparison
-        static const bool one_pass = getenv("G16_SCATTER_ONE_PASS") != nullptr;
-        if (!one_pass && slabs == 1 && max_entries * 4 > SCATTER_TWO_PASS_BYTES) {
-            uint32_t *staging = ws.scatter_stage.as<uint32_t>(2 * max_entries + 2);
-            uint32_t *part_cursor = ws.cursor.as<uint32_t>((max_entries >> k_scatter_log_part(max_entries)) + 2);
-            k_scatter_partitioned(s, n, codes, ranks, plan, offsets, max_entries, part_cursor, staging, entries);
-        } else
-        for (size_t k = 0; k < slabs; ++k) {
-            uint32_t b_lo = (uint32_t)((uint64_t)plan.nb * k / slabs), b_hi = (uint32_t)((uint64_t)plan.nb * (k + 1) / slabs);
-            k_scatter_ranked(s, n, codes, ranks, plan, offsets, b_lo, b_hi, entries);
-        }
-    } else {
-        uint32_t *cursor = ws.cursor.as<uint32_t>(total);
-        copy_d2d(cursor, offsets, total * sizeof(uint32_t), s);
-        k_scatter_by_window(s, n, codes, plan, cursor, entries);
-    }
-    dv.timer.mark(3, s);
-    // 4. bucket accumulation (the hot kernel) + fold of split buckets
+    const bool two_pass = max_entries * 4 > SCATTER_TWO_PASS_BYTES;
+    uint32_t *staging = two_pass ? ws.scatter_stage.as<uint32_t>(2 * max_entries + 2) : nullptr;
+    uint32_t *part_cursor = two_pass ? ws.cursor.as<uint32_t>((max_entries >> k_scatter_log_part(max_entries)) + 2) : nullptr;
     uint32_t *buckets = ws.buckets.as<uint32_t>(total * 4 * FieldWords<F>::N);
     uint32_t *chunk_out = ws.chunk_out.as<uint32_t>(max_split * 4 * FieldWords<F>::N);
-    uint32_t aff_rounds = affine_rounds_for(max_entries, total);
-    if (aff_rounds) {
-        // chunks of split buckets (the front of the item array) keep the XYZZ walk; every whole bucket is summed
-        // as a tree of affine additions with block-shared inversions (affine_acc.cuh)
-        uint32_t *scratch = ws.affine.as<uint32_t>(k_affine_scratch_words<F>(max_entries, total, aff_rounds));
-        k_accumulate<F>(s, max_split, pts, entries, items, bins + 1, buckets, chunk_out);
-        k_accumulate_affine<F>(s, total, pts, entries, items, bins + 1, bins + nbins, aff_rounds, scratch, max_entries, total, buckets);
-    } else {
-        k_accumulate<F>(s, max_items, pts, entries, items, bins + nbins, buckets, chunk_out);
+
+    uint32_t *d_stage = const_cast<uint32_t *>(d_scalars);   // written only when the scalars come from the host
+    // host scalars: all copies are queued first, back to back on the copy lane; `arrived[k]` fires when range k is in
+    event_t arrived[H2D_PIPE_PARTS] = {};
+    if (h_scalars && parts > 1) {
+        Device &cp = lane_of(dv, H2D_PIPE_LANE);
+        stream_wait(cp.stream, s);   // earlier work on s may still read the scalar buffer
+        for (size_t k = 0; k < parts; ++k) {
+            size_t lo = part_lo[k], cnt = part_lo[k + 1] - lo;
+            copy_h2d(d_stage + lo * 8, h_scalars + lo * 4, cnt * 32, cp.stream);
+            arrived[k] = event_record(cp.stream);
+        }
+    } else if (h_scalars) {
+        copy_h2d(d_stage, h_scalars, n * 32, s);
     }
-    k_chunk_merge<F>(s, max_split_buckets, split_list, chunk_out, buckets);
+
+    for (size_t k = 0; k < parts; ++k) {
+        const size_t lo = part_lo[k], cnt = part_lo[k + 1] - lo;
+        if (cnt == 0) continue;
+        if (h_scalars && parts > 1) event_wait_and_release(s, arrived[k]);
+        const bool add_to = k > 0;                 // later ranges continue the bucket sums of the earlier ones
+        const uint32_t *sc = d_scalars + lo * 8;
+        MsmPlan pl = plan;
+        pl.offset = (uint32_t)(first + lo);
+        const size_t n_entries = cnt * plan.nwin;
+        if (k == 0) dv.timer.mark(0, s);
+        // 1. canonical scalars -> signed digits: bucket histogram + per-window code array; the histogram atomic also
+        //    hands out the digit's rank inside its bucket
+        dev_memset(counts, 0, (total + 1) * sizeof(uint32_t), s);
+        k_digit_decompose(s, cnt, sc, mont, pl, counts, codes, ranks);
+        if (k == 0) dv.timer.mark(1, s);
+        // 2. bucket offsets (exclusive scan; offsets[total] = number of entries) and the work-item list
+        //    (bucket slices ordered by length, longest first)
+        k_exclusive_scan(s, counts, counts, total + 1, scan_tmp);
+        uint32_t *offsets = counts;
+        uint32_t item_max = (uint32_t)std::min<size_t>(k_item_max(), std::max<size_t>(ITEM_FLOOR, n_entries >> ITEM_SHIFT));
+        dev_memset(bins, 0, (nbins + 1) * sizeof(uint32_t), s);
+        k_item_count(s, total, offsets, item_max, bins);
+        k_exclusive_scan(s, bins, bins, nbins + 1, scan_tmp);
+        copy_d2d(bin_cursor, bins, (nbins + 1) * sizeof(uint32_t), s);
+        dev_memset(split_list, 0, sizeof(uint32_t), s);
+        k_item_scatter(s, total, offsets, item_max, bin_cursor, items, split_list);
+        if (k == 0) dv.timer.mark(2, s);
+        // 3. counting-sort scatter of (point index, sign) into bucket order: position = bucket offset + rank.  Entry
+        //    arrays beyond L2 go through the two-pass partitioned scatter (msm_kernels.cuh)
+        if (n_entries * 4 > SCATTER_TWO_PASS_BYTES) k_scatter_partitioned(s, cnt, codes, ranks, pl, offsets, n_entries, part_cursor, staging, entries);
+        else k_scatter_ranked(s, cnt, codes, ranks, pl, offsets, entries);
+        if (k == 0) dv.timer.mark(3, s);
+        // 4. bucket accumulation (the hot kernel) + fold of split buckets
+        size_t split_buckets = n_entries / item_max + 1, split_items = 2 * split_buckets + 16;
+        k_accumulate<F>(s, total + split_items, pts, entries, items, bins + nbins, buckets, chunk_out, add_to);
+        k_chunk_merge<F>(s, split_buckets, split_list, chunk_out, buckets, add_to, dv.sm_count);
+    }
     dv.timer.mark(4, s);
     // 5. parallel bucket reduction: thread levels while the level is work bound (every thread walks 2^log_l
     //    consecutive buckets), then block-cooperative levels (quad additions, scan + tree) for the latency
@@ -439,7 +422,7 @@ std::unique_ptr<Bases> bases_upload(Context *ctx, const uint64_t *xy, const uint
     for (size_t d = 0; d < ndev; ++d) {
         size_t begin = n * d / ndev, end = n * (d + 1) / ndev;
         BasesShard sh;
-        sh.dev = (int)d; sh.begin = begin; sh.n = end - begin; sh.owned = true;
+        sh.dev = (int)d; sh.cuda_dev = ctx->devs[d].id; sh.begin = begin; sh.n = end - begin; sh.owned = true;
         sh.pts = import_points<F>(ctx->devs[d], xy + begin * (FieldWords<F>::N), inf ? inf + begin : nullptr, sh.n);
         b->shards.push_back(sh);
     }
@@ -485,7 +468,9 @@ unsigned bases_precompute(Context *ctx, Bases *bases, unsigned c, size_t budget_
 
 // Host scalars -> host affine result over all shards of `bases`, in two halves so that several MSMs
 // can be in flight on different lanes: msm_launch issues the H2D copies and the whole pipeline of every
-// shard asynchronously, msm_finish waits, folds the per-shard partials on device 0 and returns the point.
+// shard asynchronously -- no call in it waits for a device, so the shards of a multi-device context really run
+// side by side -- and every shard sends its 192 / 384-byte partial sum straight into device 0's `partials` buffer
+// (peer copy on the shard's stream).  msm_finish makes device 0 wait for those copies, folds them and returns the point.
 template <class F>
 void msm_launch(Context *ctx, const Bases *bases, const uint64_t *scalars, size_t n, int lane,
                 uint32_t *user_xyzz = nullptr, uint32_t *user_aff = nullptr) {
@@ -495,8 +480,12 @@ void msm_launch(Context *ctx, const Bases *bases, const uint64_t *scalars, size_
     size_t nsh = bases->shards.size();
     bool user_out = user_xyzz || user_aff;   // results stay on the device (single shard only)
     if (user_out && nsh != 1) throw Error{G16_ERR_INVALID, "device outputs need unsharded bases"};
-    Device &l0 = lane_of(ctx->devs[0], lane);
-    l0.host_partials.assign(nsh * PW, 0u);
+    uint32_t *d0_parts = nullptr;
+    if (nsh > 1) {
+        Device &l0 = lane_of(ctx->devs[0], lane);
+        set_device(l0.id);
+        d0_parts = l0.ws.partials.as<uint32_t>(nsh * PW + AW);
+    }
     for (size_t k = 0; k < nsh; ++k) {
         const BasesShard &sh = bases->shards[k];
         Device &dv = lane_of(ctx->devs[sh.dev], lane);
@@ -504,35 +493,14 @@ void msm_launch(Context *ctx, const Bases *bases, const uint64_t *scalars, size_
         size_t lo = std::min(sh.begin, n), hi = std::min(sh.begin + sh.n, n);
         size_t cnt = hi - lo;
         uint32_t *d_out = dv.ws.out.as<uint32_t>(PW + AW);
-        // Large host-scalar MSMs are cut into chunks that run on separate lanes, so the H2D copy of
-        // chunk k+1 overlaps the pipeline of chunk k; the chunk partials are folded on this lane.
-        size_t chunks = cnt >= ctx->chunk_min ? H2D_CHUNKS : 1;
-        if (chunks == 1) {
-            uint32_t *d_sc = dv.ws.scalars.as<uint32_t>(cnt * 8 + 8);
-            const uint64_t *h_sc = scalars + lo * 4;   // copied inside msm_run, overlapped with the digit decomposition
-            if (nsh == 1) {
-                msm_run<F>(dv, sh, d_sc, cnt, true, ctx->c_override, user_xyzz, user_out ? user_aff : d_out + PW, lo - sh.begin, h_sc, d_sc);
-            } else {
-                msm_run<F>(dv, sh, d_sc, cnt, true, ctx->c_override, d_out, nullptr, lo - sh.begin, h_sc, d_sc);
-                copy_d2h(l0.host_partials.data() + k * PW, d_out, PW * 4, dv.stream);
-            }
+        uint32_t *d_sc = dv.ws.scalars.as<uint32_t>(cnt * 8 + 8);
+        const uint64_t *h_sc = scalars + lo * 4;   // copied inside msm_run, overlapped with the pipeline
+        if (nsh == 1) {
+            msm_run<F>(dv, sh, d_sc, cnt, true, ctx->c_override, user_xyzz, user_out ? user_aff : d_out + PW, lo - sh.begin, h_sc,
+                       ctx->h2d_pipe_min);
         } else {
-            uint32_t *d_parts = dv.ws.partials.as<uint32_t>((chunks + 2) * PW + AW);
-            for (size_t j = 0; j < chunks; ++j) {
-                size_t clo = lo + cnt * j / chunks, chi = lo + cnt * (j + 1) / chunks, ccnt = chi - clo;
-                Device &cl = lane_of(ctx->devs[sh.dev], CHUNK_LANE_BASE + lane * (int)H2D_CHUNKS + (int)j);
-                stream_wait(cl.stream, dv.stream);   // do not overtake earlier work queued on this lane
-                uint32_t *d_sc = cl.ws.scalars.as<uint32_t>(ccnt * 8 + 8);
-                copy_h2d(d_sc, scalars + clo * 4, ccnt * 32, cl.stream);
-                msm_run<F>(cl, sh, d_sc, ccnt, true, ctx->c_override, d_parts + j * PW, nullptr, clo - sh.begin);
-                stream_wait(dv.stream, cl.stream);
-            }
-            if (nsh == 1) {
-                k_partial_combine<F>(dv.stream, d_parts, (uint32_t)chunks, user_xyzz, user_out ? user_aff : d_out + PW);
-            } else {
-                k_partial_combine<F>(dv.stream, d_parts, (uint32_t)chunks, d_out, nullptr);
-                copy_d2h(l0.host_partials.data() + k * PW, d_out, PW * 4, dv.stream);
-            }
+            msm_run<F>(dv, sh, d_sc, cnt, true, ctx->c_override, d_out, nullptr, lo - sh.begin, h_sc, ctx->h2d_pipe_min);
+            copy_peer(d0_parts + k * PW, d_out, PW * 4, dv.stream);
         }
     }
 }
@@ -550,12 +518,10 @@ void msm_finish(Context *ctx, const Bases *bases, int lane, uint64_t *out_xy, ui
     } else {
         for (size_t k = 0; k < nsh; ++k) {
             Device &dv = lane_of(ctx->devs[bases->shards[k].dev], lane);
-            set_device(dv.id);
-            stream_sync(dv.stream);
+            if (&dv != &d0) stream_wait_xdev(d0.stream, d0.id, dv.stream, dv.id);
         }
         set_device(d0.id);
-        uint32_t *d_part = d0.ws.partials.as<uint32_t>(nsh * PW + AW);
-        copy_h2d(d_part, d0.host_partials.data(), nsh * PW * 4, d0.stream);
+        uint32_t *d_part = (uint32_t *)d0.ws.partials.p;
         k_partial_combine<F>(d0.stream, d_part, (uint32_t)nsh, nullptr, d_part + nsh * PW);
         copy_d2h(aff, d_part + nsh * PW, AW * 4, d0.stream);
         stream_sync(d0.stream);

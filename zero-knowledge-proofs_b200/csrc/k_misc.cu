@@ -12,8 +12,8 @@ void k_digit_decompose(stream_t s, size_t n, const uint32_t *scalars, bool mont,
     launch<DigitDecompose>(cnt, s, scalars, mont, plan, n, counts, codes, ranks, i0);
 }
 void k_scatter_ranked(stream_t s, size_t n, const uint32_t *codes, const uint32_t *ranks, MsmPlan plan,
-                      const uint32_t *offsets, uint32_t b_lo, uint32_t b_hi, uint32_t *entries) {
-    launch<ScatterRanked>(n * plan.nwin, s, codes, ranks, plan, n, offsets, b_lo, b_hi, entries);
+                      const uint32_t *offsets, uint32_t *entries) {
+    launch<ScatterRanked>(n * plan.nwin, s, codes, ranks, plan, n, offsets, entries);
 }
 // about 256 partitions of at least 2^20 entries (4 MB of `entries`): a partition stays L2 resident while pass B fills
 // it, and a block's tile leaves runs of ~16 pairs per partition, so its staging writes coalesce
@@ -40,11 +40,8 @@ void k_scatter_partitioned(stream_t s, size_t n, const uint32_t *codes, const ui
     launch<ScatterFinal>(max_entries, s, (const uint32_t *)staging, offsets + plan.total, entries);
 #else
     (void)max_entries; (void)part_cursor; (void)staging;
-    launch<ScatterRanked>(n * plan.nwin, s, codes, ranks, plan, n, offsets, 0u, plan.nb, entries);
+    launch<ScatterRanked>(n * plan.nwin, s, codes, ranks, plan, n, offsets, entries);
 #endif
-}
-void k_scatter_by_window(stream_t s, size_t n, const uint32_t *codes, MsmPlan plan, uint32_t *cursor, uint32_t *entries) {
-    launch<ScatterByWindow>(n * plan.nwin, s, codes, plan, n, cursor, entries);
 }
 size_t k_item_bins() { return ITEM_BINS; }
 size_t k_item_bytes() { return sizeof(WorkItem); }

@@ -32,14 +32,13 @@ template <> struct FieldWords<Fq2> { static constexpr size_t N = 24; static cons
 void k_digit_decompose(stream_t s, size_t n, const uint32_t *scalars, bool mont, MsmPlan plan, uint32_t *counts,
                         uint32_t *codes, uint32_t *ranks, size_t i0 = 0, size_t cnt = ~(size_t)0);
 void k_scatter_ranked(stream_t s, size_t n, const uint32_t *codes, const uint32_t *ranks, MsmPlan plan,
-                      const uint32_t *offsets, uint32_t b_lo, uint32_t b_hi, uint32_t *entries);
+                      const uint32_t *offsets, uint32_t *entries);
 // two-pass scatter through a staging area of (position, entry) pairs (device build only; see msm_kernels.cuh):
 // staging holds 2 words per entry, part_cursor k_scatter_parts(..) zeroed words
 uint32_t k_scatter_log_part(size_t max_entries);
 void k_scatter_partitioned(stream_t s, size_t n, const uint32_t *codes, const uint32_t *ranks, MsmPlan plan,
                            const uint32_t *offsets, size_t max_entries, uint32_t *part_cursor, uint32_t *staging,
                            uint32_t *entries);
-void k_scatter_by_window(stream_t s, size_t n, const uint32_t *codes, MsmPlan plan, uint32_t *cursor, uint32_t *entries);
 // work items (bucket slices ordered by length); see msm_kernels.cuh
 struct WorkItem;
 size_t k_item_bins();
@@ -52,18 +51,12 @@ size_t k_scan_tmp_words(size_t n);
 void k_exclusive_scan(stream_t s, const uint32_t *in, uint32_t *out, size_t n, uint32_t *tmp);
 
 template <class F>
+// add_to: continue the sums already stored in `buckets` (an earlier chunk of the same MSM) instead of starting at infinity
 void k_accumulate(stream_t s, size_t max_items, const uint32_t *pts, const uint32_t *entries, const WorkItem *work,
-                  const uint32_t *n_items, uint32_t *buckets, uint32_t *chunk_out);
-// bucket accumulation in affine coordinates with block-shared inversions (affine_acc.cuh): whole-bucket items
-// [*first_item, *n_items) of the item array; scratch holds k_affine_scratch_words<F>(...) words
+                  const uint32_t *n_items, uint32_t *buckets, uint32_t *chunk_out, bool add_to);
 template <class F>
-size_t k_affine_scratch_words(size_t n_entries, size_t n_buckets, uint32_t rounds);
-template <class F>
-void k_accumulate_affine(stream_t s, size_t max_items, const uint32_t *pts, const uint32_t *entries, const WorkItem *work,
-                         const uint32_t *first_item, const uint32_t *n_items, uint32_t rounds, uint32_t *scratch,
-                         size_t n_entries, size_t n_buckets, uint32_t *buckets);
-template <class F>
-void k_chunk_merge(stream_t s, size_t max_split, const uint32_t *split_list, const uint32_t *chunk_out, uint32_t *buckets);
+void k_chunk_merge(stream_t s, size_t max_split, const uint32_t *split_list, const uint32_t *chunk_out, uint32_t *buckets,
+                   bool add_to, uint32_t sm_count);
 template <class F>
 void k_reduce_level(stream_t s, size_t threads, const uint32_t *X, const uint32_t *Y, uint32_t n_in, uint32_t n_out,
                     uint32_t L, uint32_t shift, uint32_t *Xo, uint32_t *Yo);

@@ -1,55 +1,30 @@
 // Definitions of the launchers declared in kernel_api.cuh (see there).
 #pragma once
+#include <algorithm>
 #include "kernel_api.cuh"
 #include "fixed_base_kernels.cuh"
 #include "msm_kernels.cuh"
-#include "affine_acc.cuh"
 
 namespace g16 {
 
 template <class F>
 void k_accumulate(stream_t s, size_t max_items, const uint32_t *pts, const uint32_t *entries, const WorkItem *work,
-                  const uint32_t *n_items, uint32_t *buckets, uint32_t *chunk_out) {
-    launch<BucketAccumulate<F>>(max_items, s, pts, entries, work, n_items, buckets, chunk_out);
+                  const uint32_t *n_items, uint32_t *buckets, uint32_t *chunk_out, bool add_to) {
+    launch<BucketAccumulate<F>>(max_items, s, pts, entries, work, n_items, buckets, chunk_out, add_to ? 1u : 0u);
 }
 template <class F>
-size_t k_affine_scratch_words(size_t n_entries, size_t n_buckets, uint32_t rounds) {
-    size_t slots = n_buckets + AFF_INV_GROUP;   // totals (+ prefix products of the batch inversion)
-    for (uint32_t r = 0; r < rounds; ++r) slots += affine_round_slots(n_entries, n_buckets, r);
-    return slots * 2 * F::N;
-}
-template <class F>
-void k_accumulate_affine(stream_t s, size_t max_items, const uint32_t *pts, const uint32_t *entries, const WorkItem *work,
-                         const uint32_t *first_item, const uint32_t *n_items, uint32_t rounds, uint32_t *scratch,
-                         size_t n_entries, size_t n_buckets, uint32_t *buckets) {
-    if (max_items == 0) return;
-    uint32_t *totals = scratch;                                         // max_items slots
-    uint32_t *bufs = scratch + (n_buckets + AFF_INV_GROUP) * 2 * F::N;   // round buffers
-    for (uint32_t r = 0; r < rounds; ++r) {
-        launch<AffinePhase1<F>>(max_items, s, pts, entries, work, first_item, n_items, r, bufs, n_entries, n_buckets, totals);
+void k_chunk_merge(stream_t s, size_t max_split, const uint32_t *split_list, const uint32_t *chunk_out, uint32_t *buckets,
+                   bool add_to, uint32_t sm_count) {
 #ifndef G16_EMU
-        size_t inv_threads = (max_items + AFF_INV_GROUP - 1) / AFF_INV_GROUP;
-        batch_inverse_kernel<F><<<(unsigned)((inv_threads + 63) / 64), 64, 0, s>>>(totals, max_items);
-        G16_CUDA_CHECK(cudaGetLastError());
-        note_launch();
-#else
-        launch<BatchInverse<F>>((max_items + AFF_INV_GROUP - 1) / AFF_INV_GROUP, s, totals, max_items);
-#endif
-        launch<AffinePhase2<F>>(max_items, s, pts, entries, work, first_item, n_items, r, bufs, n_entries, n_buckets,
-                                (const uint32_t *)totals);
-    }
-    launch<AffineTail<F>>(max_items, s, pts, entries, work, first_item, n_items, rounds, bufs, n_entries, n_buckets, buckets);
-}
-template <class F>
-void k_chunk_merge(stream_t s, size_t max_split, const uint32_t *split_list, const uint32_t *chunk_out, uint32_t *buckets) {
-#ifndef G16_EMU
-    launch<ChunkMergeSerial<F>>(max_split, s, split_list, chunk_out, MERGE_SERIAL_MAX, buckets);
+    launch<ChunkMergeSerial<F>>(max_split, s, split_list, chunk_out, MERGE_SERIAL_MAX, buckets, add_to ? 1u : 0u);
     size_t smem = (size_t)MERGE_THREADS * 4 * F::N * sizeof(uint32_t);
-    chunk_merge_kernel<F><<<148 * 4, MERGE_THREADS, smem, s>>>(split_list, chunk_out, buckets);
+    // grid-stride over the split list: four blocks per SM of this device
+    chunk_merge_kernel<F><<<std::max(1u, sm_count) * 4, MERGE_THREADS, smem, s>>>(split_list, chunk_out, buckets, add_to ? 1u : 0u);
     G16_CUDA_CHECK(cudaGetLastError());
     note_launch();
 #else
-    launch<ChunkMergeSerial<F>>(max_split, s, split_list, chunk_out, 0xffffffffu, buckets);
+    (void)sm_count;
+    launch<ChunkMergeSerial<F>>(max_split, s, split_list, chunk_out, 0xffffffffu, buckets, add_to ? 1u : 0u);
 #endif
 }
 template <class F>

@@ -66,8 +66,7 @@ struct DigitDecompose {
                 uint32_t b = (uint32_t)(d < 0 ? -d : d) - 1u;
                 // the histogram atomic also hands out this digit's rank inside its bucket, so the scatter
                 // pass needs no second round of atomics (position = bucket offset + rank)
-                uint32_t rank = atomic_add_u32(&counts[(plan.bwin == 1 ? 0u : w) * plan.nb + b], 1u);
-                if (ranks) ranks[(size_t)w * n + i] = rank;
+                ranks[(size_t)w * n + i] = atomic_add_u32(&counts[(plan.bwin == 1 ? 0u : w) * plan.nb + b], 1u);
                 code = b | (d < 0 ? 0x80000000u : 0u);
             }
             codes[(size_t)w * n + i] = code;
@@ -75,32 +74,15 @@ struct DigitDecompose {
     }
 };
 
-// Counting-sort scatter, one thread per (window, scalar), window-major: all writes of one window land
-// in an n x 4 B slice of `entries` (64 MB at n = 2^24, i.e. L2 resident) before the next window starts.
-// entries[cursor[bucket]++] = point index | sign << 31
-struct ScatterByWindow {
-    static constexpr int BLOCK = 256;
-    G16_HD static void run(size_t t, const uint32_t *codes, MsmPlan plan, size_t n, uint32_t *cursor, uint32_t *entries) {
-        uint32_t code = codes[t];
-        if (code == NO_DIGIT) return;
-        uint32_t w = (uint32_t)(t / n), i = (uint32_t)(t % n);
-        uint32_t pos = atomic_add_u32(&cursor[(plan.bwin == 1 ? 0u : w) * plan.nb + (code & 0x7fffffffu)], 1u);
-        entries[pos] = (w * plan.stride + plan.offset + i) | (code & 0x80000000u);
-    }
-};
-
-// Same scatter with the ranks recorded by DigitDecompose: no atomics, position = offset + rank.
+// Counting-sort scatter with the ranks recorded by DigitDecompose, one thread per (window, scalar), window-major:
+// no atomics, position = bucket offset + rank, entries[position] = point index | sign << 31.  Used while the entry
+// array fits L2 (the scattered 4-byte writes merge there); larger arrays take the two-pass kernel below.
 struct ScatterRanked {
     static constexpr int BLOCK = 256;
-    // Only buckets in [b_lo, b_hi) are written by one launch: the engine sweeps the bucket range in slabs
-    // whose slice of `entries` fits in L2, so the scattered 4-byte writes merge there instead of each
-    // dirtying a DRAM sector (the code stream is re-read once per slab -- coalesced and cheap).
     G16_HD static void run(size_t t, const uint32_t *codes, const uint32_t *ranks, MsmPlan plan, size_t n,
-                           const uint32_t *offsets, uint32_t b_lo, uint32_t b_hi, uint32_t *entries) {
+                           const uint32_t *offsets, uint32_t *entries) {
         uint32_t code = codes[t];
         if (code == NO_DIGIT) return;
-        uint32_t b = code & 0x7fffffffu;
-        if (b < b_lo || b >= b_hi) return;
         uint32_t w = (uint32_t)(t / n), i = (uint32_t)(t % n);
         uint32_t pos = offsets[(plan.bwin == 1 ? 0u : w) * plan.nb + (code & 0x7fffffffu)] + ranks[t];
         entries[pos] = (w * plan.stride + plan.offset + i) | (code & 0x80000000u);
@@ -400,15 +382,18 @@ G16_HD XYZZ<F> load_xyzz(const uint32_t *src, size_t idx) {
 
 // The hot kernel: one thread per work item.  Whole buckets are written straight to `buckets`; chunks of
 // split buckets go to chunk_out[item index] (split items occupy the front of the item array) and are
-// folded by ChunkMerge.
+// folded by ChunkMerge.  add_to != 0: the call continues an MSM whose earlier scalar chunks already left their
+// sums in `buckets` (host scalars arrive in pieces, engine.cuh) -- start from the stored sum, skip empty slices.
 template <class F>
 struct BucketAccumulate {
     static constexpr int BLOCK = 128;
     G16_HD static void run(size_t t, const uint32_t *pts, const uint32_t *entries, const WorkItem *items,
-                           const uint32_t *n_items, uint32_t *buckets, uint32_t *chunk_out) {
+                           const uint32_t *n_items, uint32_t *buckets, uint32_t *chunk_out, uint32_t add_to) {
         if (t >= *n_items) return;   // the launch covers an upper bound; the exact count lives on the device
         WorkItem it = items[t];
-        XYZZ<F> acc = XYZZ<F>::inf();
+        const bool resume = add_to && !(it.bucket & SPLIT_FLAG);
+        if (resume && it.begin == it.end) return;
+        XYZZ<F> acc = resume ? load_xyzz<F>(buckets, it.bucket) : XYZZ<F>::inf();
         for (uint32_t e = it.begin; e < it.end; ++e) {
             uint32_t v = entries[e];
             Affine<F> p = load_affine<F>(pts, v & 0x7fffffffu);
@@ -427,7 +412,7 @@ constexpr uint32_t MERGE_SERIAL_MAX = 16;   // buckets with more chunks than thi
 constexpr int MERGE_THREADS = 64;
 template <class F>
 __global__ void __launch_bounds__(MERGE_THREADS) chunk_merge_kernel(const uint32_t *split_list, const uint32_t *chunk_out,
-                                                                    uint32_t *buckets) {
+                                                                    uint32_t *buckets, uint32_t add_to) {
     extern __shared__ uint32_t sm[];
     const int T = MERGE_THREADS, j = threadIdx.x;
     const uint32_t n_split = split_list[0];
@@ -453,7 +438,13 @@ __global__ void __launch_bounds__(MERGE_THREADS) chunk_merge_kernel(const uint32
             }
             __syncthreads();
         }
-        if (j == 0) store_xyzz<F>(buckets, g, acc);
+        if (j == 0) {
+            if (add_to) {
+                XYZZ<F> prev = load_xyzz<F>(buckets, g);
+                xyzz_add_call(acc, prev);
+            }
+            store_xyzz<F>(buckets, g, acc);
+        }
     }
 }
 #endif
@@ -463,11 +454,11 @@ template <class F>
 struct ChunkMergeSerial {
     static constexpr int BLOCK = 64;
     G16_HD static void run(size_t k, const uint32_t *split_list, const uint32_t *chunk_out, uint32_t serial_max,
-                           uint32_t *buckets) {
+                           uint32_t *buckets, uint32_t add_to) {
         if (k >= split_list[0]) return;
         uint32_t g = split_list[1 + 3 * k], first = split_list[2 + 3 * k], nch = split_list[3 + 3 * k];
         if (nch > serial_max) return;
-        XYZZ<F> acc = XYZZ<F>::inf();
+        XYZZ<F> acc = add_to ? load_xyzz<F>(buckets, g) : XYZZ<F>::inf();
         for (uint32_t c = 0; c < nch; ++c) {
             XYZZ<F> p = load_xyzz<F>(chunk_out, first + c);
             xyzz_add_call(acc, p);

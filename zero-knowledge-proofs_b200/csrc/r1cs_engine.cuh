@@ -30,13 +30,14 @@ struct StackedCsr {
 };
 
 struct R1cs {
-    Context *ctx = nullptr;
+    Context *ctx = nullptr;        // identity check only; never dereferenced after upload
     int dev = 0;
+    int cuda_dev = 0;              // CUDA ordinal of the device that holds the matrices
     size_t m = 0, nv = 0;          // constraints, variables
     uint32_t log_n = 0;            // domain = next_power_of_two(m)  (`QAP::from_r1cs`, qap/src/lib.rs:100)
     StackedCsr rows, cols;         // by constraint (prove) / by variable (setup)
     ~R1cs() {
-        if (ctx) set_device(ctx->devs[dev].id);
+        set_device_nothrow(cuda_dev);
         rows.release(); cols.release();
     }
 };
@@ -66,8 +67,9 @@ inline void upload_stacked(Device &dv, const HostCsr &h, StackedCsr &d) {
 }
 
 // mats[k] = {row_ptr (m + 1), col (nnz_k), val (nnz_k x 4 u64)} for k = A, B, C.  Entries whose variable index
-// is >= num_variables are dropped like the reference does (qap/src/lib.rs:121-138); a (row, variable) pair
-// must appear at most once per matrix (the reference's linear combinations are maps).
+// is >= num_variables are dropped like the reference does (qap/src/lib.rs:121-138).  When a (row, variable) pair
+// appears more than once in a matrix the LAST value wins, as in the reference's `a_evals[row][var] = coeff`
+// assignment loop (qap/src/lib.rs:121-138) -- the SpMV kernels would otherwise sum the duplicates.
 struct CsrView { const uint32_t *row_ptr, *col; const uint64_t *val; };
 inline std::unique_ptr<R1cs> r1cs_upload(Context *ctx, size_t m, size_t nv, const CsrView mats[3]) {
     if (nv == 0) throw Error{G16_ERR_INVALID, "R1CS needs at least the constant variable"};
@@ -80,17 +82,22 @@ inline std::unique_ptr<R1cs> r1cs_upload(Context *ctx, size_t m, size_t nv, cons
     HostCsr by_row, by_col;
     by_row.ptr.assign(3 * m + 1, 0);
     by_col.ptr.assign(3 * nv + 1, 0);
-    // pass 1: count the kept entries per row line and per column line
+    // pass 1: count the kept entries per row line and per column line.  seen[var] = 1 + line of the last row that
+    // mentioned var: a repeated (row, variable) pair is counted once
+    std::vector<uint64_t> seen(nv, 0);
     uint64_t kept = 0;
     for (int k = 0; k < 3; ++k) {
         const CsrView &v = mats[k];
         if (m && (!v.row_ptr || v.row_ptr[0] != 0)) throw Error{G16_ERR_INVALID, "row_ptr must start at 0"};
         for (size_t i = 0; i < m; ++i) {
             if (v.row_ptr[i + 1] < v.row_ptr[i]) throw Error{G16_ERR_INVALID, "row_ptr must be non-decreasing"};
+            const uint64_t line = (uint64_t)k * m + i + 1;
             for (uint32_t e = v.row_ptr[i]; e < v.row_ptr[i + 1]; ++e) {
-                if (v.col[e] >= nv) continue;
+                uint32_t c = v.col[e];
+                if (c >= nv || seen[c] == line) continue;
+                seen[c] = line;
                 ++by_row.ptr[k * m + i + 1];
-                ++by_col.ptr[k * nv + v.col[e] + 1];
+                ++by_col.ptr[k * nv + c + 1];
                 ++kept;
             }
         }
@@ -101,23 +108,38 @@ inline std::unique_ptr<R1cs> r1cs_upload(Context *ctx, size_t m, size_t nv, cons
     by_row.idx.resize(kept); by_row.val.resize(kept * 4);
     by_col.idx.resize(kept); by_col.val.resize(kept * 4);
     std::vector<uint32_t> cur(by_col.ptr.begin(), by_col.ptr.end() - 1);
+    // pass 2: fill; slot_row / slot_col remember where the pair of the current line went, so that a later duplicate
+    // overwrites the value in place
+    std::fill(seen.begin(), seen.end(), 0);
+    std::vector<uint32_t> slot_row(nv, 0), slot_col(nv, 0);
     size_t w = 0;
     for (int k = 0; k < 3; ++k) {
         const CsrView &v = mats[k];
-        for (size_t i = 0; i < m; ++i)
+        for (size_t i = 0; i < m; ++i) {
+            const uint64_t line = (uint64_t)k * m + i + 1;
             for (uint32_t e = v.row_ptr[i]; e < v.row_ptr[i + 1]; ++e) {
                 uint32_t c = v.col[e];
                 if (c >= nv) continue;
+                if (seen[c] == line) {
+                    memcpy(&by_row.val[4 * (size_t)slot_row[c]], v.val + 4 * (size_t)e, 32);
+                    memcpy(&by_col.val[4 * (size_t)slot_col[c]], v.val + 4 * (size_t)e, 32);
+                    continue;
+                }
+                seen[c] = line;
                 by_row.idx[w] = c;
                 memcpy(&by_row.val[4 * w], v.val + 4 * (size_t)e, 32);
+                slot_row[c] = (uint32_t)w;
                 ++w;
                 uint32_t p = cur[k * nv + c]++;
                 by_col.idx[p] = (uint32_t)i;
                 memcpy(&by_col.val[4 * (size_t)p], v.val + 4 * (size_t)e, 32);
+                slot_col[c] = p;
             }
+        }
     }
     Device &dv = ctx->devs[0];
     set_device(dv.id);
+    r->cuda_dev = dv.id;
     upload_stacked(dv, by_row, r->rows);
     upload_stacked(dv, by_col, r->cols);
     return r;

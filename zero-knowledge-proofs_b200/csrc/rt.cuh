@@ -111,6 +111,33 @@ inline void stream_wait(stream_t waiter, stream_t producer) {
 #endif
 }
 
+// explicit event handles for waits that are queued later than the point they refer to
+#ifndef G16_EMU
+typedef cudaEvent_t event_t;
+#else
+typedef void *event_t;
+#endif
+inline event_t event_record(stream_t producer) {
+#ifndef G16_EMU
+    cudaEvent_t ev;
+    G16_CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    cudaError_t e = cudaEventRecord(ev, producer);
+    if (e != cudaSuccess) { cudaEventDestroy(ev); G16_CUDA_CHECK(e); }
+    return ev;
+#else
+    (void)producer; return nullptr;
+#endif
+}
+inline void event_wait_and_release(stream_t waiter, event_t ev) {
+#ifndef G16_EMU
+    cudaError_t e = cudaStreamWaitEvent(waiter, ev, 0);
+    cudaEventDestroy(ev);   // released once the wait has been satisfied
+    G16_CUDA_CHECK(e);
+#else
+    (void)waiter; (void)ev;
+#endif
+}
+
 // the same across devices: the event is created and recorded on the producer's device, the wait is queued on the
 // waiter's; the current device is left at the waiter's
 inline void stream_wait_xdev(stream_t waiter, int waiter_dev, stream_t producer, int producer_dev) {

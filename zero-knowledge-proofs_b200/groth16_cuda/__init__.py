@@ -32,7 +32,7 @@ G1_AFFINE_WORDS, G2_AFFINE_WORDS = 25, 49
 
 EXPORTS = [
     "g16_version", "g16_device_count", "g16_ctx_create", "g16_ctx_destroy", "g16_last_error",
-    "g16_ctx_set_stream", "g16_ctx_synchronize", "g16_ctx_set_window_bits", "g16_ctx_set_affine_rounds",
+    "g16_ctx_set_stream", "g16_ctx_synchronize", "g16_ctx_set_window_bits", "g16_ctx_set_h2d_pipeline_min",
     "g16_g1_bases_upload", "g16_g2_bases_upload", "g16_g1_bases_from_device", "g16_g2_bases_from_device",
     "g16_bases_free", "g16_bases_len", "g16_bases_precompute",
     "g16_g1_msm", "g16_g2_msm", "g16_g1_msm_oneshot", "g16_g2_msm_oneshot",
@@ -102,7 +102,7 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.g16_ctx_set_stream.argtypes = [vp, vp]
     lib.g16_ctx_synchronize.argtypes = [vp]
     lib.g16_ctx_set_window_bits.argtypes = [vp, ctypes.c_uint]
-    lib.g16_ctx_set_affine_rounds.argtypes = [vp, ctypes.c_int]
+    lib.g16_ctx_set_h2d_pipeline_min.argtypes = [vp, sz]
     for g in ("g1", "g2"):
         getattr(lib, f"g16_{g}_bases_upload").argtypes = [vp, vp, vp, sz, ctypes.POINTER(vp)]
         getattr(lib, f"g16_{g}_bases_from_device").argtypes = [vp, vp, sz, ctypes.POINTER(vp)]
@@ -119,6 +119,7 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.g16_bases_len.argtypes = [vp]
     lib.g16_bases_len.restype = sz
     lib.g16_pk_upload.argtypes = [vp, ctypes.POINTER(_PkHost), ctypes.POINTER(vp)]
+    lib.g16_pk_precompute.argtypes = [vp, vp]
     lib.g16_pk_free.argtypes = [vp]
     lib.g16_pk_free.restype = None
     lib.g16_prove.argtypes = [vp, vp, vp, sz, vp, sz, vp, vp, vp, vp, vp, vp, vp, vp]
@@ -266,9 +267,9 @@ class Context:
     def set_window_bits(self, c: int):
         self._check(self.lib.g16_ctx_set_window_bits(self.handle, c))
 
-    def set_affine_rounds(self, rounds: int):
-        """Pairwise affine rounds of the bucket sums (-1 = auto, 0 = XYZZ walk only); process-wide tuning."""
-        self._check(self.lib.g16_ctx_set_affine_rounds(self.handle, rounds))
+    def set_h2d_pipeline_min(self, min_scalars: int):
+        """Host-scalar MSMs of at least this many scalars per device pipeline their H2D copy (0 = default 2^19)."""
+        self._check(self.lib.g16_ctx_set_h2d_pipeline_min(self.handle, min_scalars))
 
     # ---- bases
     def _upload(self, g: str, xy, inf) -> Bases:
@@ -420,6 +421,10 @@ class Context:
         h = ctypes.c_void_p()
         self._check(self.lib.g16_pk_upload(self.handle, ctypes.byref(s), ctypes.byref(h)))
         return ProvingKeyDevice(self, h.value)
+
+    def pk_precompute(self, pk: ProvingKeyDevice):
+        """One-time tables of multiples for the five resident arrays (g16_pk_precompute)."""
+        self._check(self.lib.g16_pk_precompute(self.handle, pk.handle))
 
     def prove(self, pk: ProvingKeyDevice, assignment_fr, h_coeffs, r, s):
         """Group part of Prover::prove.  Returns ((a_xy, a_inf), (b_xy, b_inf), (c_xy, c_inf))."""

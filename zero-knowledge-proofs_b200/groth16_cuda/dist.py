@@ -14,10 +14,19 @@ def shard_range(n: int, rank: int, world: int):
     return n * rank // world, n * (rank + 1) // world
 
 
-def msm_sharded(ctx, group: str, bases, scalars_ptr: int, n_local: int, partial, gathered, out, world: int):
-    """partial / gathered / out: int32 torch tensors on the rank's device (48 / 48*world / 25 words for G1)."""
+def msm_sharded(ctx, group: str, bases, scalars_ptr: int, n_local: int, partial, gathered, out, world: int,
+                always_gather: bool = False):
+    """partial / gathered / out: int32 torch tensors on the rank's device (48 / 48*world / 25 words for G1).
+
+    Stream ordering is part of this function: the context is switched to torch's CURRENT stream first
+    (`Context.set_stream`, it stays there afterwards), because `all_gather_into_tensor` orders itself against that
+    stream only -- the MSM that writes `partial`, the collective that reads it and the fold that reads `gathered`
+    are then one in-order sequence.  A context left on its private stream would let NCCL read `partial` early.
+    always_gather: run the all-gather + fold even when world == 1 (tests)."""
+    import torch
     import torch.distributed as dist
-    if world == 1:
+    ctx.set_stream(torch.cuda.current_stream(partial.device).cuda_stream)
+    if world == 1 and not always_gather:
         ctx.msm_device(group, bases, scalars_ptr, n_local, out.data_ptr(), 0)
         return
     ctx.msm_device(group, bases, scalars_ptr, n_local, 0, partial.data_ptr())
