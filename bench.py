@@ -223,7 +223,7 @@ def run_reference(args):
               f"as the GPU arm); ark's window rule gives c = {c_s} ({-(-255 // c_s)} windows) at the sample size and c = {c_f} "
               f"({-(-255 // c_f)} windows) at 2^{args.log_n}, so the full-size CPU rate is about "
               f"{(-(-255 // c_s)) / (-(-255 // c_f)):.2f}x the sampled one")
-    prove_log_m = 13
+    prove_log_m = 16
     prove_s = cpu_prove_sample(oracle, prove_log_m, threads)
     line = {
         "impl": "reference", "metric": "g1_msm_points_per_sec", "value": value, "unit": "points/s",
@@ -348,7 +348,7 @@ def prove_record(args, oracle, devices, log_n, steps, with_setup):
     finally:
         ctx.close()
     if not args.no_cpu_baseline:
-        log_m = 13
+        log_m = 16
         cpu_s = cpu_prove_sample(oracle, log_m, th)
         out["cpu_baseline"] = {"kind": "port", "cores": th, "ms_sample": cpu_s * 1e3,
                                "sample": f"the same five MSMs on a synthetic 2^{log_m} key (C port of ark-ec 0.4.2 msm)",

@@ -18,6 +18,24 @@ def test_library_is_the_cuda_build(gpu_ctx):
     assert gpu_ctx.lib.g16_device_count() >= 1
 
 
+def test_c_caller_through_the_abi(oracle, gens, tmp_path):
+    """A caller written in C (tests/c_harness/abi_harness.c, built against include/g16_cuda.h): one-shot seam and the
+    resident + precomputed path return the oracle's bytes."""
+    import subprocess
+    import groth16_cuda
+    import test_abi_exports
+    n = 3000
+    pts, inf, sc = helpers.adversarial(oracle, gens, "g1", 0xc0ffee, n)
+    exp, einf = oracle.g1_msm(pts, inf, sc, threads=oracle.max_threads())
+    path = tmp_path / "msm_case.bin"
+    with open(path, "wb") as f:
+        f.write(np.uint64(n).tobytes()); f.write(pts.tobytes()); f.write(inf.tobytes()); f.write(sc.tobytes())
+        f.write(exp.tobytes()); f.write(np.uint8(einf).tobytes())
+    exe = test_abi_exports.build_c_harness(groth16_cuda.DEFAULT_LIB, tmp_path)
+    out = subprocess.run([exe, "msm", str(path)], capture_output=True, text=True)
+    assert out.returncode == 0 and "msm ok" in out.stdout, out.stdout + out.stderr
+
+
 def test_field_ops_on_device(gpu_ctx, oracle):
     pc.check_debug_field(gpu_ctx, oracle, n=200000)
 

@@ -384,9 +384,22 @@ G16_HD XYZZ<F> load_xyzz(const uint32_t *src, size_t idx) {
 // split buckets go to chunk_out[item index] (split items occupy the front of the item array) and are
 // folded by ChunkMerge.  add_to != 0: the call continues an MSM whose earlier scalar chunks already left their
 // sums in `buckets` (host scalars arrive in pieces, engine.cuh) -- start from the stored sum, skip empty slices.
+// Launch shape of the hot kernel.  Shipped values: 128 threads, the register allocation left to ptxas (G1: 164
+// registers = 3 blocks per SM, G2: 255 = 2 blocks).  tools/lab_build.py builds A/B variants of the library with other
+// values (-DG16_ACC_BLOCK=.. -DG16_ACC_MIN_BLOCKS_G1=.. -DG16_ACC_MIN_BLOCKS_G2=..) for tools/bench_stages.py --lib.
+#ifndef G16_ACC_BLOCK
+#define G16_ACC_BLOCK 128
+#endif
+#ifndef G16_ACC_MIN_BLOCKS_G1
+#define G16_ACC_MIN_BLOCKS_G1 1
+#endif
+#ifndef G16_ACC_MIN_BLOCKS_G2
+#define G16_ACC_MIN_BLOCKS_G2 1
+#endif
 template <class F>
 struct BucketAccumulate {
-    static constexpr int BLOCK = 128;
+    static constexpr int BLOCK = G16_ACC_BLOCK;
+    static constexpr int MIN_BLOCKS = F::N == 12 ? G16_ACC_MIN_BLOCKS_G1 : G16_ACC_MIN_BLOCKS_G2;
     G16_HD static void run(size_t t, const uint32_t *pts, const uint32_t *entries, const WorkItem *items,
                            const uint32_t *n_items, uint32_t *buckets, uint32_t *chunk_out, uint32_t add_to) {
         if (t >= *n_items) return;   // the launch covers an upper bound; the exact count lives on the device

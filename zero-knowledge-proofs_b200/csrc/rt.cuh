@@ -177,9 +177,13 @@ void note_launch();  // defined in k_misc.cu (one counter for all translation un
 unsigned long long launch_count();
 
 // ---- launch of a per-thread body -------------------------------------------------------
+// A body may declare `static constexpr int MIN_BLOCKS` (resident blocks per SM the register allocation must allow,
+// the second argument of __launch_bounds__); bodies without it get 1.
+template <class Body, class = void> struct MinBlocksOf { static constexpr int value = 1; };
+template <class Body> struct MinBlocksOf<Body, decltype((void)Body::MIN_BLOCKS)> { static constexpr int value = Body::MIN_BLOCKS; };
 #ifndef G16_EMU
 template <class Body, class... A>
-__global__ void __launch_bounds__(Body::BLOCK) thread_kernel(size_t n, A... args) {
+__global__ void __launch_bounds__(Body::BLOCK, MinBlocksOf<Body>::value) thread_kernel(size_t n, A... args) {
     size_t t = (size_t)blockIdx.x * Body::BLOCK + threadIdx.x;
     if (t < n) Body::run(t, args...);
 }

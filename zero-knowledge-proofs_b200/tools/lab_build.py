@@ -1,0 +1,65 @@
+#!/usr/bin/env python
+"""A/B variants of libg16cuda.so for kernel experiments (NOT shipped, NOT loaded by the product binding).
+
+    python zero-knowledge-proofs_b200/tools/lab_build.py            # builds every variant below into lib/lab/<name>.so
+    python zero-knowledge-proofs_b200/tools/bench_stages.py --group g2 --log-n 20 --lib zero-knowledge-proofs_b200/lib/lab/<name>.so
+
+A variant recompiles the listed translation units with extra -D flags and links them with the standard objects of
+lib/obj (build.py must have run).  The knobs are plain compile-time constants with the shipped values as defaults
+(csrc/msm_kernels.cuh): the library itself has one code path and reads no environment variable."""
+import concurrent.futures as cf
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, HERE)
+import build as b  # noqa: E402
+
+LAB = os.path.join(b.LIBDIR, "lab")
+VARIANTS = {
+    # name: {unit: [flags]}
+    "g2_mb3": {"k_acc_g2.cu": ["-DG16_ACC_MIN_BLOCKS_G2=3"]},
+    "g2_b64_mb4": {"k_acc_g2.cu": ["-DG16_ACC_BLOCK=64", "-DG16_ACC_MIN_BLOCKS_G2=4"]},
+    "g2_b64_mb6": {"k_acc_g2.cu": ["-DG16_ACC_BLOCK=64", "-DG16_ACC_MIN_BLOCKS_G2=6"]},
+    "g1_mb4": {"k_acc_g1.cu": ["-DG16_ACC_MIN_BLOCKS_G1=4"]},
+    "g1_b64_mb6": {"k_acc_g1.cu": ["-DG16_ACC_BLOCK=64", "-DG16_ACC_MIN_BLOCKS_G1=6"]},
+    "g1_b64_mb8": {"k_acc_g1.cu": ["-DG16_ACC_BLOCK=64", "-DG16_ACC_MIN_BLOCKS_G1=8"]},
+}
+
+
+def build_variant(name, units):
+    os.makedirs(os.path.join(LAB, "obj"), exist_ok=True)
+    std_units = sorted(os.path.basename(p) for p in __import__("glob").glob(os.path.join(b.CSRC, "*.cu")))
+    objs = []
+    for u in std_units:
+        if u in units:
+            obj = os.path.join(LAB, "obj", f"{name}_{u.replace('.cu', '.o')}")
+            cmd = [b.NVCC] + b.ARCH + b.COMMON + units[u] + ["-c", os.path.join(b.CSRC, u), "-o", obj]
+            res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+            open(obj + ".log", "w").write(res.stdout)
+            if res.returncode:
+                raise RuntimeError(res.stdout[-3000:])
+            stats = [l for l in res.stdout.splitlines() if "BucketAccumulate" in l or "Used" in l or "spill" in l]
+            # the lines that follow the BucketAccumulate entry
+            for i, l in enumerate(res.stdout.splitlines()):
+                if "Compiling entry function" in l and "BucketAccumulate" in l:
+                    print(f"[{name}]", " | ".join(x.strip() for x in res.stdout.splitlines()[i + 2:i + 4]))
+            objs.append(obj)
+        else:
+            objs.append(os.path.join(b.OBJDIR, u.replace(".cu", ".o")))
+    out = os.path.join(LAB, name + ".so")
+    subprocess.run([b.NVCC] + b.ARCH + ["-shared", "-o", out] + objs, check=True)
+    return out
+
+
+def main():
+    b.build()
+    names = sys.argv[1:] or list(VARIANTS)
+    with cf.ThreadPoolExecutor(max_workers=min(len(names), os.cpu_count() or 4)) as ex:
+        for out in ex.map(lambda n: build_variant(n, VARIANTS[n]), names):
+            print(out)
+
+
+if __name__ == "__main__":
+    main()
