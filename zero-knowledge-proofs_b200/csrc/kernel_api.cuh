@@ -78,9 +78,18 @@ void k_import_bases(stream_t s, size_t n, const uint32_t *xy, const uint8_t *inf
 template <class F>
 void k_export_flags(stream_t s, size_t n, const uint32_t *pts, uint8_t *inf);
 
+// Fixed-base windows: signed digits of FB_BITS bits, d in [-(2^(FB_BITS-1) - 1), 2^(FB_BITS-1)], so a window's table holds
+// the 2^(FB_BITS-1) positive multiples only (the sign flips y).  16 bits: 16 mixed additions per scalar, tables of
+// 16 x 32768 affine points = 50 MB (G1) / 100 MB (G2) per base, L2 resident on B200 (126 MB).  The host-emulation build
+// (tests only) walks the same code with 8-bit windows: its one-thread-at-a-time loop cannot build 2^19 table entries.
+#ifndef G16_EMU
+constexpr uint32_t FB_BITS = 16;
+#else
 constexpr uint32_t FB_BITS = 8;
-constexpr uint32_t FB_WINDOWS = 256 / FB_BITS;         // 32
-constexpr uint32_t FB_ENTRIES = (1u << FB_BITS) - 1u;  // 255 non-zero digits per window
+#endif
+constexpr uint32_t FB_WINDOWS = 256 / FB_BITS;         // 16
+constexpr uint32_t FB_ENTRIES = 1u << (FB_BITS - 1);   // multiples 1 .. 2^(FB_BITS-1) of 2^(FB_BITS j) * base
+constexpr uint32_t FB_TABLE_GROUP = 8;                 // consecutive table entries one thread builds (shared inversion)
 template <class F>
 void k_fb_powers(stream_t s, const uint32_t *base_xy, uint32_t *powers);
 template <class F>

@@ -384,14 +384,18 @@ G16_HD XYZZ<F> load_xyzz(const uint32_t *src, size_t idx) {
 // split buckets go to chunk_out[item index] (split items occupy the front of the item array) and are
 // folded by ChunkMerge.  add_to != 0: the call continues an MSM whose earlier scalar chunks already left their
 // sums in `buckets` (host scalars arrive in pieces, engine.cuh) -- start from the stored sum, skip empty slices.
-// Launch shape of the hot kernel.  Shipped values: 128 threads, the register allocation left to ptxas (G1: 164
-// registers = 3 blocks per SM, G2: 255 = 2 blocks).  tools/lab_build.py builds A/B variants of the library with other
-// values (-DG16_ACC_BLOCK=.. -DG16_ACC_MIN_BLOCKS_G1=.. -DG16_ACC_MIN_BLOCKS_G2=..) for tools/bench_stages.py --lib.
+// Launch shape of the hot kernel.  Shipped values: 64 threads per block; G1 six blocks per SM (166 registers, no spill),
+// G2 left to ptxas (255 registers = 4 blocks of 64).  Measured on B200 at 2^24 (profiles/r02_run2_lab_g1_acc_launch_shape_2p24.txt):
+// 128 threads 76.1 ms, 128 x 4 blocks (128 registers) 75.3, 64 x 6 blocks 73.1, 64 x 8 blocks (128 registers) 75.8 -- the
+// smaller block lets the length-sorted items of a block finish closer together.  G2 at 2^20: 16.6 ms either way, and
+// forcing three blocks of 128 (168 registers, 1.8 KB of spills) costs 22.7 ms.  tools/lab_build.py builds A/B variants of
+// the library with other values (-DG16_ACC_BLOCK=.. -DG16_ACC_MIN_BLOCKS_G1=.. -DG16_ACC_MIN_BLOCKS_G2=..) for
+// tools/bench_stages.py --lib.
 #ifndef G16_ACC_BLOCK
-#define G16_ACC_BLOCK 128
+#define G16_ACC_BLOCK 64
 #endif
 #ifndef G16_ACC_MIN_BLOCKS_G1
-#define G16_ACC_MIN_BLOCKS_G1 1
+#define G16_ACC_MIN_BLOCKS_G1 6
 #endif
 #ifndef G16_ACC_MIN_BLOCKS_G2
 #define G16_ACC_MIN_BLOCKS_G2 1
@@ -517,6 +521,50 @@ struct ReduceLevel {
         store_xyzz<F>(Yo, (size_t)w * n_out + g, acc);
     }
 };
+
+// The same level with a quad of lanes per group (device build, see quad.cuh): every addition is the 4-lane cooperative
+// one, so the 2 L dependent additions of a group cost 4 instead of 14 multiplication latencies each and the kernel needs
+// half the registers of the one-thread form (G2: 255 registers and 4.7 KB of spills there).  Used for G2, where the
+// thread form ran at a quarter of the multiplier peak; G1's thread form is within 20 % of it and stays.
+#if !defined(G16_EMU) && defined(__CUDACC__)
+template <class F>
+__global__ void __launch_bounds__(128) reduce_level_quad_kernel(size_t groups, const uint32_t *X, const uint32_t *Y, uint32_t n_in,
+                                                                uint32_t n_out, uint32_t L, uint32_t shift, uint32_t *Xo, uint32_t *Yo) {
+    const int q = threadIdx.x & 3;
+    const size_t t = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+    const bool live = t < groups;                       // dead quads of the last warp walk the loops with points at infinity
+    const uint32_t w = live ? (uint32_t)(t / n_out) : 0u, g = live ? (uint32_t)(t % n_out) : 0u;
+    const size_t base = (size_t)w * n_in;
+    const uint32_t lo = g * L;
+    const uint32_t hi = live ? (lo + L < n_in ? lo + L : n_in) : lo;
+    XYZZ<F> running = XYZZ<F>::inf(), acc = XYZZ<F>::inf();
+#pragma unroll 1
+    for (uint32_t k = L; k-- > 1;) {                    // i = lo + k, top down; warp-uniform trip count
+        uint32_t i = lo + k;
+        XYZZ<F> x = i < hi ? load_xyzz<F>(X, base + i) : XYZZ<F>::inf();
+        xyzz_add_quad(running, x, q);
+        xyzz_add_quad(acc, running, q);
+    }
+    {
+        XYZZ<F> x0 = lo < hi ? load_xyzz<F>(X, base + lo) : XYZZ<F>::inf();
+        xyzz_add_quad(running, x0, q);
+    }
+#pragma unroll 1
+    for (uint32_t s = 0; s < shift; ++s) xyzz_dbl_quad(acc, q);
+    if (Y) {
+#pragma unroll 1
+        for (uint32_t k = 0; k < L; ++k) {
+            uint32_t i = lo + k;
+            XYZZ<F> y = i < hi ? load_xyzz<F>(Y, base + i) : XYZZ<F>::inf();
+            xyzz_add_quad(acc, y, q);
+        }
+    }
+    if (live && q == 0) {
+        store_xyzz<F>(Xo, (size_t)w * n_out + g, running);
+        store_xyzz<F>(Yo, (size_t)w * n_out + g, acc);
+    }
+}
+#endif
 
 // Block-cooperative level of the same reduction for the upper, latency-bound part of the tree.  From here
 // on a level carries THREE arrays: X (to be weighted by index), Y1 (weighted partials produced by the X

@@ -25,7 +25,8 @@ def msm_sharded(ctx, group: str, bases, scalars_ptr: int, n_local: int, partial,
     always_gather: run the all-gather + fold even when world == 1 (tests)."""
     import torch
     import torch.distributed as dist
-    ctx.set_stream(torch.cuda.current_stream(partial.device).cuda_stream)
+    if partial.is_cuda:   # (the gloo / host-emulation tests pass CPU tensors: synchronous, nothing to order)
+        ctx.set_stream(torch.cuda.current_stream(partial.device).cuda_stream)
     if world == 1 and not always_gather:
         ctx.msm_device(group, bases, scalars_ptr, n_local, out.data_ptr(), 0)
         return

@@ -15,6 +15,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--bits", type=int, default=255)
     ap.add_argument("--no-precompute", action="store_true")
+    ap.add_argument("--precompute-bits", type=int, default=0)
     ap.add_argument("--lib", default=None, help="alternative build of the library (A/B experiments)")
     a = ap.parse_args()
     import torch, bls12_381 as bls, cpu_oracle as oracle, groth16_cuda
@@ -39,7 +40,7 @@ def main():
     pre = 0
     t0 = time.perf_counter()
     if not a.no_precompute:
-        pre = bases.precompute(0)
+        pre = bases.precompute(a.precompute_bits)
     torch.cuda.synchronize()
     pre_ms = (time.perf_counter() - t0) * 1e3
     out = torch.zeros(49, dtype=torch.int32, device=dev)

@@ -18,13 +18,13 @@ import build as b  # noqa: E402
 
 LAB = os.path.join(b.LIBDIR, "lab")
 VARIANTS = {
-    # name: {unit: [flags]}
-    "g2_mb3": {"k_acc_g2.cu": ["-DG16_ACC_MIN_BLOCKS_G2=3"]},
-    "g2_b64_mb4": {"k_acc_g2.cu": ["-DG16_ACC_BLOCK=64", "-DG16_ACC_MIN_BLOCKS_G2=4"]},
-    "g2_b64_mb6": {"k_acc_g2.cu": ["-DG16_ACC_BLOCK=64", "-DG16_ACC_MIN_BLOCKS_G2=6"]},
-    "g1_mb4": {"k_acc_g1.cu": ["-DG16_ACC_MIN_BLOCKS_G1=4"]},
-    "g1_b64_mb6": {"k_acc_g1.cu": ["-DG16_ACC_BLOCK=64", "-DG16_ACC_MIN_BLOCKS_G1=6"]},
-    "g1_b64_mb8": {"k_acc_g1.cu": ["-DG16_ACC_BLOCK=64", "-DG16_ACC_MIN_BLOCKS_G1=8"]},
+    # name: {unit: [flags]}   (shipped: 64 threads, G1 6 blocks per SM, G2 unconstrained)
+    "g1_b128": {"k_acc_g1.cu": ["-DG16_ACC_BLOCK=128", "-DG16_ACC_MIN_BLOCKS_G1=1"]},
+    "g1_b32_mb12": {"k_acc_g1.cu": ["-DG16_ACC_BLOCK=32", "-DG16_ACC_MIN_BLOCKS_G1=12"]},
+    "g1_b64_mb7": {"k_acc_g1.cu": ["-DG16_ACC_BLOCK=64", "-DG16_ACC_MIN_BLOCKS_G1=7"]},
+    "g1_b96_mb4": {"k_acc_g1.cu": ["-DG16_ACC_BLOCK=96", "-DG16_ACC_MIN_BLOCKS_G1=4"]},
+    "g2_b128": {"k_acc_g2.cu": ["-DG16_ACC_BLOCK=128"]},
+    "g2_b32": {"k_acc_g2.cu": ["-DG16_ACC_BLOCK=32"]},
 }
 
 
