@@ -225,15 +225,24 @@ constexpr uint32_t REDUCE_LOG_L = 5;
 // and the longest item would set the kernel's duration: max(ITEM_FLOOR, entries >> ITEM_SHIFT).  Floor 16: at
 // 2^16 / 2^18 pairs the 2^15 buckets alone are too few threads, cutting them into slices of <= 16 / 32 entries takes
 // the accumulation from 0.79 to 0.70 ms and from 2.39 to 2.02 ms (profiles/README.md run 23)
-constexpr size_t ITEM_FLOOR = 16;
+#ifndef G16_ITEM_FLOOR
+#define G16_ITEM_FLOOR 16
+#endif
+constexpr size_t ITEM_FLOOR = G16_ITEM_FLOOR;   // (tools/lab_build.py overrides the G16_* constants for A/B builds)
 constexpr unsigned ITEM_SHIFT = 17;
 // Levels with at most 2^tile_max_log2 entries run block-cooperatively; a thread level aims to leave 2^groups_log2 groups
 // behind.  Measured on B200 (profiles/README.md run 19): 15 / 15 is best up to 2^20 buckets (reduce 1.14 -> 0.99 ms at 2^19
 // buckets), 17 / 16 beyond (3.07 -> 3.00 ms at 2^21).
+#ifndef G16_RED_GROUPS_LOG2
+#define G16_RED_GROUPS_LOG2 15
+#endif
+#ifndef G16_RED_TILE_MAX_LOG2
+#define G16_RED_TILE_MAX_LOG2 15
+#endif
 inline void reduce_split(size_t buckets, size_t &tile_level_max, size_t &thread_level_groups) {
     bool big = buckets > ((size_t)1 << 20);
-    thread_level_groups = (size_t)1 << (big ? 17 : 15);
-    tile_level_max = (size_t)1 << (big ? 16 : 15);
+    thread_level_groups = (size_t)1 << (big ? 17 : G16_RED_GROUPS_LOG2);
+    tile_level_max = (size_t)1 << (big ? 16 : G16_RED_TILE_MAX_LOG2);
 }
 
 // One MSM on one device, asynchronous on dv.stream.

@@ -30,15 +30,6 @@ void k_chunk_merge(stream_t s, size_t max_split, const uint32_t *split_list, con
 template <class F>
 void k_reduce_level(stream_t s, size_t threads, const uint32_t *X, const uint32_t *Y, uint32_t n_in, uint32_t n_out,
                     uint32_t L, uint32_t shift, uint32_t *Xo, uint32_t *Yo) {
-#ifndef G16_EMU
-    if constexpr (F::N > 12) {   // G2: one quad of lanes per group (msm_kernels.cuh)
-        if (threads == 0) return;
-        size_t blocks = (threads * 4 + 127) / 128;
-        reduce_level_quad_kernel<F><<<(unsigned)blocks, 128, 0, s>>>(threads, X, Y, n_in, n_out, L, shift, Xo, Yo);
-        G16_CUDA_CHECK(cudaGetLastError());
-        note_launch();
-    } else
-#endif
     launch<ReduceLevel<F>>(threads, s, X, Y, n_in, n_out, L, shift, Xo, Yo);
 }
 template <class F>

@@ -522,49 +522,9 @@ struct ReduceLevel {
     }
 };
 
-// The same level with a quad of lanes per group (device build, see quad.cuh): every addition is the 4-lane cooperative
-// one, so the 2 L dependent additions of a group cost 4 instead of 14 multiplication latencies each and the kernel needs
-// half the registers of the one-thread form (G2: 255 registers and 4.7 KB of spills there).  Used for G2, where the
-// thread form ran at a quarter of the multiplier peak; G1's thread form is within 20 % of it and stays.
-#if !defined(G16_EMU) && defined(__CUDACC__)
-template <class F>
-__global__ void __launch_bounds__(128) reduce_level_quad_kernel(size_t groups, const uint32_t *X, const uint32_t *Y, uint32_t n_in,
-                                                                uint32_t n_out, uint32_t L, uint32_t shift, uint32_t *Xo, uint32_t *Yo) {
-    const int q = threadIdx.x & 3;
-    const size_t t = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
-    const bool live = t < groups;                       // dead quads of the last warp walk the loops with points at infinity
-    const uint32_t w = live ? (uint32_t)(t / n_out) : 0u, g = live ? (uint32_t)(t % n_out) : 0u;
-    const size_t base = (size_t)w * n_in;
-    const uint32_t lo = g * L;
-    const uint32_t hi = live ? (lo + L < n_in ? lo + L : n_in) : lo;
-    XYZZ<F> running = XYZZ<F>::inf(), acc = XYZZ<F>::inf();
-#pragma unroll 1
-    for (uint32_t k = L; k-- > 1;) {                    // i = lo + k, top down; warp-uniform trip count
-        uint32_t i = lo + k;
-        XYZZ<F> x = i < hi ? load_xyzz<F>(X, base + i) : XYZZ<F>::inf();
-        xyzz_add_quad(running, x, q);
-        xyzz_add_quad(acc, running, q);
-    }
-    {
-        XYZZ<F> x0 = lo < hi ? load_xyzz<F>(X, base + lo) : XYZZ<F>::inf();
-        xyzz_add_quad(running, x0, q);
-    }
-#pragma unroll 1
-    for (uint32_t s = 0; s < shift; ++s) xyzz_dbl_quad(acc, q);
-    if (Y) {
-#pragma unroll 1
-        for (uint32_t k = 0; k < L; ++k) {
-            uint32_t i = lo + k;
-            XYZZ<F> y = i < hi ? load_xyzz<F>(Y, base + i) : XYZZ<F>::inf();
-            xyzz_add_quad(acc, y, q);
-        }
-    }
-    if (live && q == 0) {
-        store_xyzz<F>(Xo, (size_t)w * n_out + g, running);
-        store_xyzz<F>(Yo, (size_t)w * n_out + g, acc);
-    }
-}
-#endif
+// (A variant of this level with one quad of lanes per group -- every addition the 4-lane cooperative one of quad.cuh --
+// was measured for G2 and lost: bucket reduction 5.79 ms against 5.31 ms at 2^19 buckets,
+// profiles/r02_run3_lab_g2_quad_reduce_and_window_sweep_2p20.txt.  Not in the library.)
 
 // Block-cooperative level of the same reduction for the upper, latency-bound part of the tree.  From here
 // on a level carries THREE arrays: X (to be weighted by index), Y1 (weighted partials produced by the X

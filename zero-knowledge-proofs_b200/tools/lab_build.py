@@ -17,14 +17,21 @@ sys.path.insert(0, HERE)
 import build as b  # noqa: E402
 
 LAB = os.path.join(b.LIBDIR, "lab")
+ENGINE_UNITS = ("api.cu", "api_r1cs.cu", "api_wire.cu")   # translation units that include engine.cuh
+
+
+def engine(*flags):
+    return {u: list(flags) for u in ENGINE_UNITS}
+
+
 VARIANTS = {
-    # name: {unit: [flags]}   (shipped: 64 threads, G1 6 blocks per SM, G2 unconstrained)
-    "g1_b128": {"k_acc_g1.cu": ["-DG16_ACC_BLOCK=128", "-DG16_ACC_MIN_BLOCKS_G1=1"]},
-    "g1_b32_mb12": {"k_acc_g1.cu": ["-DG16_ACC_BLOCK=32", "-DG16_ACC_MIN_BLOCKS_G1=12"]},
-    "g1_b64_mb7": {"k_acc_g1.cu": ["-DG16_ACC_BLOCK=64", "-DG16_ACC_MIN_BLOCKS_G1=7"]},
-    "g1_b96_mb4": {"k_acc_g1.cu": ["-DG16_ACC_BLOCK=96", "-DG16_ACC_MIN_BLOCKS_G1=4"]},
-    "g2_b128": {"k_acc_g2.cu": ["-DG16_ACC_BLOCK=128"]},
-    "g2_b32": {"k_acc_g2.cu": ["-DG16_ACC_BLOCK=32"]},
+    # name: {unit: [flags]}   (shipped: accumulate 64 threads x 6 blocks (G1); item floor 16; reduction split 15 / 15)
+    "item_floor8": engine("-DG16_ITEM_FLOOR=8"),
+    "item_floor32": engine("-DG16_ITEM_FLOOR=32"),
+    "red_14_15": engine("-DG16_RED_GROUPS_LOG2=14"),
+    "red_14_14": engine("-DG16_RED_GROUPS_LOG2=14", "-DG16_RED_TILE_MAX_LOG2=14"),
+    "red_16_15": engine("-DG16_RED_GROUPS_LOG2=16"),
+    "red_13_13": engine("-DG16_RED_GROUPS_LOG2=13", "-DG16_RED_TILE_MAX_LOG2=13"),
 }
 
 
