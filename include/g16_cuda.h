@@ -160,10 +160,15 @@ int g16_prove(g16_ctx *ctx, const g16_pk *pk, const uint64_t *assignment_fr, siz
  * (a_evals[i] = <A-row i, assignment>; rows beyond the constraint count are zero).  Same polynomial as
  * `QAP::compute_quotient_polynomial` (crates/groth16-qap/src/lib.rs:225-271, called at
  * crates/groth16-core/src/lib.rs:200) for a satisfying assignment.  n must be a power of two; all arrays
- * are n x 4 u64 Montgomery Fr; h_coeffs receives n coefficients (the top one is zero).  Returns
+ * are n x 4 u64 Montgomery Fr; h_coeffs receives n coefficients (the top one is zero).  The four buffers may be
+ * pageable or pinned host memory (pinned: the copies run at PCIe rate and asynchronously to the host).  Returns
  * G16_ERR_INVALID ("Polynomial division failed") when A*B - C does not vanish on the domain. */
 int g16_quotient_h(g16_ctx *ctx, const uint64_t *a_evals, const uint64_t *b_evals, const uint64_t *c_evals, size_t n,
                    uint64_t *h_coeffs);
+/* Device in / device out, asynchronous on the ctx stream (single-device ctx): dev_abc = the evaluations of A, B, C
+ * back to back (3 n x 4 u64, OVERWRITTEN), dev_h receives the n coefficients, *dev_bad_rows (one u32 on the device)
+ * the number of domain points where A*B != C (0 = the division is exact). */
+int g16_quotient_h_device(g16_ctx *ctx, void *dev_abc, size_t n, void *dev_h, void *dev_bad_rows);
 
 /* ---- sparse R1CS: setup and prove for real circuits (rows 1-3 chained on the device) -------- */
 /* The reference turns an R1CS into dense per-variable polynomials (`QAP::from_r1cs`,

@@ -638,6 +638,19 @@ int g16_quotient_h(g16_ctx *ctx, const uint64_t *a_evals, const uint64_t *b_eval
     });
 }
 
+int g16_quotient_h_device(g16_ctx *ctx, void *dev_abc, size_t n, void *dev_h, void *dev_bad_rows) {
+    if (!ctx) return G16_ERR_INVALID;
+    return guarded(ctx, [&] {
+        Device &dv = single_device(ctx);
+        require(dev_abc && dev_h && dev_bad_rows, "NULL argument");
+        require(n >= 1 && (n & (n - 1)) == 0 && n <= ((size_t)1 << 28), "domain size must be a power of two <= 2^28");
+        uint32_t log_n = 0;
+        while (((size_t)1 << log_n) < n) ++log_n;
+        dev_memset(dev_bad_rows, 0, 4, dv.stream);
+        quotient_device(dv, log_n, (uint32_t *)dev_abc, (uint32_t *)dev_bad_rows, (uint32_t *)dev_h);
+    });
+}
+
 // ---- test hooks --------------------------------------------------------------------------------
 unsigned long long g16_launch_count(void) { return launch_count(); }
 

@@ -550,15 +550,17 @@ void msm_host(Context *ctx, const Bases *bases, const uint64_t *scalars, size_t 
 //   evals: host, 3 arrays (a, b, c) of n Fr each (Montgomery), n = 2^log_n;  h: host, n Fr
 // Returns false when A*B - C does not vanish on the domain (the reference's PolynomialDivisionFailed).
 // ---------------------------------------------------------------------------------------
-// constants + twiddles of the size-2^log_n domain, cached per workspace
+// constants, twiddles and scale tables of the size-2^log_n domain, cached per workspace.
+// ntt_tw layout (Fr elements): tw[n/2] | twi[n/2] | scale[n] | fscale[n]
 inline const uint32_t *ntt_prepare(Device &dv, uint32_t log_n) {
     Workspace &ws = dv.ws;
     uint32_t n = 1u << log_n;
-    uint32_t *tw = ws.ntt_tw.as<uint32_t>((size_t)n * 8 + 8);       // tw[n/2] then twi[n/2]
+    uint32_t *tw = ws.ntt_tw.as<uint32_t>((size_t)n * 24 + 8);
     uint32_t *consts = ws.ntt_consts.as<uint32_t>(k_ntt_const_words());
     if (ws.ntt_log_n != log_n) {
         k_ntt_setup(dv.stream, log_n, consts);
         if (n >= 2) k_ntt_twiddles(dv.stream, n, consts, tw, tw + (size_t)(n / 2) * 8);
+        k_ntt_scale_tables(dv.stream, n, log_n, consts, tw + (size_t)n * 8, tw + (size_t)n * 16);
         ws.ntt_log_n = log_n;
     }
     return consts;
@@ -570,14 +572,14 @@ inline void quotient_device(Device &dv, uint32_t log_n, uint32_t *abc, uint32_t 
     uint32_t n = 1u << log_n;
     const uint32_t *consts = ntt_prepare(dv, log_n);
     const uint32_t *tw = (const uint32_t *)dv.ws.ntt_tw.p, *twi = tw + (size_t)(n / 2) * 8;
+    const uint32_t *scale = tw + (size_t)n * 8, *fscale = tw + (size_t)n * 16;
     k_ntt_check_vanish(s, abc, n, flag);
-    // coefficients (bit-reversed), coset shift, values on the coset
-    for (uint32_t half = n / 2; half >= 1; half >>= 1) k_ntt_stage(s, false, 3, abc, twi, n, half);
-    k_ntt_coset_scale(s, 3, abc, consts, n, log_n);
-    for (uint32_t half = 1; half < n; half <<= 1) k_ntt_stage(s, true, 3, abc, tw, n, half);
+    // coefficients (bit-reversed) with the coset shift folded into the last pass, then values on the coset
+    k_ntt_transform(s, false, 3, abc, twi, log_n, scale);
+    k_ntt_transform(s, true, 3, abc, tw, log_n, nullptr);
     k_ntt_quotient_pointwise(s, abc, consts, n);
-    for (uint32_t half = n / 2; half >= 1; half >>= 1) k_ntt_stage(s, false, 1, abc, twi, n, half);
-    k_ntt_final_scale(s, abc, consts, n, log_n, out);
+    k_ntt_transform(s, false, 1, abc, twi, log_n, nullptr);
+    k_ntt_final_permute(s, abc, fscale, n, log_n, out);
 }
 inline bool quotient_host(Device &dv, const uint64_t *a, const uint64_t *b, const uint64_t *c, uint32_t log_n, uint64_t *h) {
     Workspace &ws = dv.ws;

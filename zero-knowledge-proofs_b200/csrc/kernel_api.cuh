@@ -102,9 +102,12 @@ size_t k_ntt_const_words();
 void k_ntt_setup(stream_t s, uint32_t log_n, uint32_t *consts);
 void k_ntt_twiddles(stream_t s, uint32_t n, const uint32_t *consts, uint32_t *tw, uint32_t *twi);
 void k_ntt_stage(stream_t s, bool dit, size_t batch, uint32_t *x, const uint32_t *tw, uint32_t n, uint32_t half);
-void k_ntt_coset_scale(stream_t s, size_t batch, uint32_t *x, const uint32_t *consts, uint32_t n, uint32_t log_n);
+// whole transform (fused stages on the device); scale: optional per-position factors applied with a DIF transform
+void k_ntt_transform(stream_t s, bool dit, size_t batch, uint32_t *x, const uint32_t *tw, uint32_t log_n, const uint32_t *scale);
+// scale[p] = g^br(p) / n, fscale[j] = g^-j / n (cached per domain size next to the twiddles)
+void k_ntt_scale_tables(stream_t s, uint32_t n, uint32_t log_n, const uint32_t *consts, uint32_t *scale, uint32_t *fscale);
+void k_ntt_final_permute(stream_t s, const uint32_t *x, const uint32_t *fscale, uint32_t n, uint32_t log_n, uint32_t *out);
 void k_ntt_quotient_pointwise(stream_t s, uint32_t *abc, const uint32_t *consts, uint32_t n);
-void k_ntt_final_scale(stream_t s, const uint32_t *x, const uint32_t *consts, uint32_t n, uint32_t log_n, uint32_t *out);
 void k_ntt_check_vanish(stream_t s, const uint32_t *abc, uint32_t n, uint32_t *flag);
 
 // sparse R1CS (Fr), see r1cs_kernels.cuh.  Stacked CSR: `lines` lines, out[(t / seg) * seg_out + t % seg]

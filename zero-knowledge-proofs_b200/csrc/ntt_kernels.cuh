@@ -11,9 +11,9 @@
 // Domain = ark-poly's Radix2EvaluationDomain: omega = TWO_ADIC_ROOT^(2^(32 - log n)), TWO_ADIC_ROOT =
 // 7^((r-1)/2^32); coset generator g = 7 (any g outside the domain gives the same H).
 //
-// Transforms: decimation-in-frequency forward (natural in, bit-reversed out) and decimation-in-time
-// (bit-reversed in, natural out), so no separate permutation pass is needed; one kernel per stage, one
-// thread per butterfly (the stages stream 64 B per butterfly: HBM bound).
+// Transforms: decimation-in-frequency (natural in, bit-reversed out) and decimation-in-time (bit-reversed in, natural
+// out), so no separate permutation pass is needed.  On the device up to seven consecutive stages run on a tile held in
+// shared memory (ntt_fused_kernel); the one-stage kernels state the same butterflies for the host emulation build.
 #pragma once
 #include "fp.cuh"
 #include "kernel_api.cuh"
@@ -123,13 +123,128 @@ struct NttStageDit {
     }
 };
 
-// coefficients in bit-reversed order (after the inverse DIF): x[p] *= g^(br(p)) / n
-struct NttCosetScale {
+// ---- fused stages (device build) ---------------------------------------------------------------------------------
+// The kernels above stream the whole array through HBM once per stage (64 B per butterfly per stage).  Here a block
+// keeps a tile of 2^S rows x C columns in shared memory and runs S consecutive stages on it, so a transform of 2^20
+// points makes 3 passes over HBM instead of 20.  Same butterflies, same twiddle table, same element order as the
+// one-stage kernels -- the results are bit-identical.  Stage k (k = 0 .. log_n - 1) has half = n >> (k + 1); a pass
+// covers stages k0 .. k0 + S - 1, whose butterfly network couples the 2^S elements
+//     i = B * 2^S * stride + r * stride + off,   r < 2^S,   stride = n >> (k0 + S),   off < stride, B < 2^k0.
+// Middle passes (stride >= C) take C consecutive offsets as columns (C * 32 B contiguous per row); the innermost pass
+// (stride = 1) takes C consecutive blocks B as columns (the tile is 2^S * C contiguous elements).
+#if !defined(G16_EMU) && defined(__CUDACC__)
+constexpr int NTT_FUSED_THREADS = 256;
+constexpr uint32_t NTT_FUSED_MAX_STAGES = 7;
+constexpr uint32_t NTT_FUSED_MAX_COLS = 8;
+__device__ __forceinline__ Fr fr_load4(const uint32_t *p) {
+    Fr r;
+    const uint4 *q = reinterpret_cast<const uint4 *>(p);
+    uint4 a = q[0], b = q[1];
+    r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w; r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+    return r;
+}
+__device__ __forceinline__ void fr_store4(uint32_t *p, const Fr &v) {
+    uint4 *q = reinterpret_cast<uint4 *>(p);
+    q[0] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+    q[1] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+}
+// x: `batch` arrays of n elements back to back; tw: omega^k (DIT, forward) or omega^-k (DIF, inverse), k < n / 2.
+// scale (optional, DIF innermost pass or DIT first pass): per-element factors applied when the tile is stored (DIF) /
+// loaded (DIT) -- the coset shift g^(br(p)) / n of the bit-reversed coefficients, see NttCosetTable.
+static __global__ void __launch_bounds__(NTT_FUSED_THREADS) ntt_fused_kernel(uint32_t *x, const uint32_t *tw, uint32_t log_n, uint32_t k0,
+                                                                             uint32_t S, uint32_t log_c, uint32_t tiles_per_array,
+                                                                             int dit, const uint32_t *scale) {
+    extern __shared__ uint4 ntt_tile4[];
+    uint32_t *tile = reinterpret_cast<uint32_t *>(ntt_tile4);
+    const uint32_t n = 1u << log_n, R = 1u << S, C = 1u << log_c;
+    const uint32_t log_stride = log_n - k0 - S, stride = 1u << log_stride;
+    const uint32_t arr = blockIdx.x / tiles_per_array, t = blockIdx.x % tiles_per_array;
+    uint32_t *xa = x + (size_t)arr * n * 8;
+    const bool inner = log_stride == 0;
+    // element (r, c) of the tile lives at base(c) + r * stride
+    uint32_t base0, off0 = 0;
+    if (inner) base0 = (t << log_c) << S;                                   // block B = t C + c, index B R + r
+    else {
+        uint32_t per = stride >> log_c;                                     // tiles per block B
+        uint32_t B = t / per;
+        off0 = (t % per) << log_c;
+        base0 = ((B << S) << log_stride) + off0;
+    }
+    const uint32_t elems = R << log_c;
+    // load: consecutive threads walk the contiguous direction (rows when inner, columns otherwise)
+    for (uint32_t e = threadIdx.x; e < elems; e += NTT_FUSED_THREADS) {
+        uint32_t r, c;
+        size_t gi;
+        if (inner) { r = e & (R - 1); c = e >> S; gi = (size_t)base0 + ((size_t)c << S) + r; }
+        else { c = e & (C - 1); r = e >> log_c; gi = (size_t)base0 + ((size_t)r << log_stride) + c; }
+        Fr v = fr_load4(xa + gi * 8);
+        if (dit && scale) v = Fr::mul(v, fr_load4(scale + gi * 8));
+        fr_store4(tile + ((size_t)(r << log_c) + c) * 8, v);
+    }
+    __syncthreads();
+    const uint32_t bfs = elems >> 1;
+    for (uint32_t s = 0; s < S; ++s) {
+        // DIF walks the local half R/2 .. 1, DIT 1 .. R/2
+        const uint32_t log_lh = dit ? s : S - 1 - s, lh = 1u << log_lh;
+        const uint32_t log_h = log_lh + log_stride;                         // global half of this stage
+        const uint32_t tw_shift = log_n - 1 - log_h;                        // twiddle index = j << tw_shift
+        for (uint32_t bf = threadIdx.x; bf < bfs; bf += NTT_FUSED_THREADS) {
+            uint32_t c = bf & (C - 1), pr = bf >> log_c;
+            uint32_t jr = pr & (lh - 1), r0 = ((pr >> log_lh) << (log_lh + 1)) + jr;
+            uint32_t j = inner ? jr : (jr << log_stride) + off0 + c;
+            uint32_t *p0 = tile + ((size_t)(r0 << log_c) + c) * 8, *p1 = p0 + ((size_t)lh << log_c) * 8;
+            Fr u = fr_load4(p0), v = fr_load4(p1), w = fr_load4(tw + ((size_t)j << tw_shift) * 8);
+            if (dit) {
+                v = Fr::mul(v, w);
+                fr_store4(p0, Fr::add(u, v));
+                fr_store4(p1, Fr::sub(u, v));
+            } else {
+                fr_store4(p0, Fr::add(u, v));
+                fr_store4(p1, Fr::mul(Fr::sub(u, v), w));
+            }
+        }
+        __syncthreads();
+    }
+    for (uint32_t e = threadIdx.x; e < elems; e += NTT_FUSED_THREADS) {
+        uint32_t r, c;
+        size_t gi;
+        if (inner) { r = e & (R - 1); c = e >> S; gi = (size_t)base0 + ((size_t)c << S) + r; }
+        else { c = e & (C - 1); r = e >> log_c; gi = (size_t)base0 + ((size_t)r << log_stride) + c; }
+        Fr v = fr_load4(tile + ((size_t)(r << log_c) + c) * 8);
+        if (!dit && scale) v = Fr::mul(v, fr_load4(scale + gi * 8));
+        fr_store4(xa + gi * 8, v);
+    }
+}
+#endif
+
+// scale[p] = g^(br(p)) / n for p < n: the factor the coset shift applies to the bit-reversed coefficient p.  Built once
+// per domain size (cached with the twiddles), so the shift costs one multiplication per element inside the fused pass
+// instead of a ~log n multiplication power ladder per element per prove.
+struct NttCosetTable {
     static constexpr int BLOCK = 128;
-    G16_HD static void run(size_t t, uint32_t *x, const uint32_t *consts, uint32_t n, uint32_t log_n) {
-        uint32_t p = (uint32_t)(t % n);
-        Fr s = Fr::mul(pow_from_table(consts, 64, bitrev(p, log_n)), fr_load(consts, 128));
-        fr_store(x, t, Fr::mul(fr_load(x, t), s));
+    G16_HD static void run(size_t p, const uint32_t *consts, uint32_t log_n, uint32_t *scale) {
+        fr_store(scale, p, Fr::mul(pow_from_table(consts, 64, bitrev((uint32_t)p, log_n)), fr_load(consts, 128)));
+    }
+};
+// x[t] *= scale[t mod n] (the emulation build and n = 1 apply the table with a kernel of its own)
+struct NttCosetScaleTable {
+    static constexpr int BLOCK = 128;
+    G16_HD static void run(size_t t, uint32_t *x, const uint32_t *scale, uint32_t n) {
+        fr_store(x, t, Fr::mul(fr_load(x, t), fr_load(scale, t % n)));
+    }
+};
+// fscale[j] = g^-j / n for j < n (the factor of output coefficient j)
+struct NttFinalTable {
+    static constexpr int BLOCK = 128;
+    G16_HD static void run(size_t j, const uint32_t *consts, uint32_t *fscale) {
+        fr_store(fscale, j, Fr::mul(pow_from_table(consts, 96, (uint32_t)j), fr_load(consts, 128)));
+    }
+};
+// out[j] = x[br(j)] * fscale[j]
+struct NttFinalPermute {
+    static constexpr int BLOCK = 128;
+    G16_HD static void run(size_t j, const uint32_t *x, const uint32_t *fscale, uint32_t log_n, uint32_t *out) {
+        fr_store(out, j, Fr::mul(fr_load(x, bitrev((uint32_t)j, log_n)), fr_load(fscale, j)));
     }
 };
 
@@ -139,15 +254,6 @@ struct NttQuotientPointwise {
     G16_HD static void run(size_t i, uint32_t *abc, const uint32_t *consts, uint32_t n) {
         Fr a = fr_load(abc, i), b = fr_load(abc, (size_t)n + i), c = fr_load(abc, 2 * (size_t)n + i);
         fr_store(abc, i, Fr::mul(Fr::sub(Fr::mul(a, b), c), fr_load(consts, 129)));
-    }
-};
-
-// out[j] = x[br(j)] * g^-j / n   (x = inverse DIF of h~, bit-reversed)
-struct NttFinalScale {
-    static constexpr int BLOCK = 128;
-    G16_HD static void run(size_t j, const uint32_t *x, const uint32_t *consts, uint32_t log_n, uint32_t *out) {
-        Fr s = Fr::mul(pow_from_table(consts, 96, (uint32_t)j), fr_load(consts, 128));
-        fr_store(out, j, Fr::mul(fr_load(x, bitrev((uint32_t)j, log_n)), s));
     }
 };
 

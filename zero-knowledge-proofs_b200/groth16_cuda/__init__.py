@@ -40,7 +40,7 @@ EXPORTS = [
     "g16_g1_combine_partials_device", "g16_g2_combine_partials_device",
     "g16_g1_fixed_base_mul", "g16_g2_fixed_base_mul",
     "g16_g1_fixed_base_mul_device", "g16_g2_fixed_base_mul_device",
-    "g16_pk_upload", "g16_pk_free", "g16_prove", "g16_pk_precompute", "g16_quotient_h",
+    "g16_pk_upload", "g16_pk_free", "g16_prove", "g16_pk_precompute", "g16_quotient_h", "g16_quotient_h_device",
     "g16_r1cs_upload", "g16_r1cs_free", "g16_r1cs_domain_size", "g16_r1cs_domain_evals", "g16_r1cs_eval_at",
     "g16_setup_crs", "g16_prove_r1cs",
     "g16_g1_serialize", "g16_g2_serialize", "g16_g1_deserialize", "g16_g2_deserialize",
@@ -124,6 +124,7 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.g16_pk_free.restype = None
     lib.g16_prove.argtypes = [vp, vp, vp, sz, vp, sz, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.g16_quotient_h.argtypes = [vp, vp, vp, vp, sz, vp]
+    lib.g16_quotient_h_device.argtypes = [vp, vp, sz, vp, vp]
     lib.g16_r1cs_upload.argtypes = [vp, sz, sz, ctypes.POINTER(_Csr), ctypes.POINTER(_Csr), ctypes.POINTER(_Csr),
                                     ctypes.POINTER(vp)]
     lib.g16_r1cs_free.argtypes = [vp]
@@ -378,15 +379,21 @@ class Context:
         self._check(getattr(self.lib, f"g16_{g}_fixed_base_mul_device")(self.handle, _ptr(base_xy), dev_scalars, n, dev_out))
 
     # ---- quotient polynomial
-    def quotient_h(self, a_evals, b_evals, c_evals) -> np.ndarray:
-        """H = (A*B - C) / (x^n - 1) from domain evaluations (QAP::compute_quotient_polynomial); n x 4 u64."""
+    def quotient_h(self, a_evals, b_evals, c_evals, out=None) -> np.ndarray:
+        """H = (A*B - C) / (x^n - 1) from domain evaluations (QAP::compute_quotient_polynomial); n x 4 u64.
+        out: caller-owned n x 4 uint64 result buffer (e.g. pinned host memory: pinned buffers are copied at PCIe rate)."""
         a, b, c = (_u64(x, 4) for x in (a_evals, b_evals, c_evals))
         n = a.shape[0]
         if b.shape[0] != n or c.shape[0] != n:
             raise MSMError(G16_ERR_LENGTH, "evaluation vectors differ in length")
-        h = np.zeros((n, 4), dtype=np.uint64)
+        h = np.zeros((n, 4), dtype=np.uint64) if out is None else out
+        assert h.dtype == np.uint64 and h.shape == (n, 4) and h.flags.c_contiguous
         self._check(self.lib.g16_quotient_h(self.handle, _ptr(a), _ptr(b), _ptr(c), n, _ptr(h)))
         return h
+
+    def quotient_h_device(self, dev_abc: int, n: int, dev_h: int, dev_bad_rows: int):
+        """Device pointers (e.g. torch.Tensor.data_ptr()): abc = A, B, C evaluations back to back (overwritten)."""
+        self._check(self.lib.g16_quotient_h_device(self.handle, dev_abc, n, dev_h, dev_bad_rows))
 
     # ---- prove
     def pk_upload(self, pk: dict) -> ProvingKeyDevice:

@@ -308,6 +308,13 @@ pub fn quotient_h(ctx: &Context, a: &[Fr], b: &[Fr], c: &[Fr]) -> Result<Vec<Fr>
     Ok(unpack_scalars(&out))
 }
 
+/// Device in / device out form of `quotient_h`, asynchronous on the context stream.
+/// # Safety
+/// `dev_abc`: 3 n x 4 u64 on the device (overwritten), `dev_h`: n x 4 u64, `dev_bad_rows`: one u32, all on the context's device.
+pub unsafe fn quotient_h_device(ctx: &Context, dev_abc: *mut c_void, n: usize, dev_h: *mut c_void, dev_bad_rows: *mut c_void) -> Result<(), String> {
+    check(ctx.raw, g16_quotient_h_device(ctx.raw, dev_abc, n, dev_h, dev_bad_rows))
+}
+
 // ---- sparse R1CS: setup and prove for real circuits ---------------------------------------------------------
 /// One constraint matrix in CSR form over the constraints: `row_ptr[num_constraints + 1]`, `col[nnz]` (variable
 /// indices), `val[nnz]`.  Build it from `R1CS::constraints[i].a.terms` etc. (`crates/groth16-r1cs`).

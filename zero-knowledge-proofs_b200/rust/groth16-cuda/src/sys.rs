@@ -87,6 +87,7 @@ extern "C" {
                      r: *const u64, s: *const u64, a_xy: *mut u64, a_inf: *mut u8, b_xy: *mut u64, b_inf: *mut u8, c_xy: *mut u64, c_inf: *mut u8) -> c_int;
     // ---- quotient polynomial
     pub fn g16_quotient_h(ctx: *mut g16_ctx, a_evals: *const u64, b_evals: *const u64, c_evals: *const u64, n: usize, h_coeffs: *mut u64) -> c_int;
+    pub fn g16_quotient_h_device(ctx: *mut g16_ctx, dev_abc: *mut c_void, n: usize, dev_h: *mut c_void, dev_bad_rows: *mut c_void) -> c_int;
     // ---- sparse R1CS
     pub fn g16_r1cs_upload(ctx: *mut g16_ctx, num_constraints: usize, num_variables: usize, a: *const g16_csr, b: *const g16_csr, c: *const g16_csr, out: *mut *mut g16_r1cs) -> c_int;
     pub fn g16_r1cs_free(r1cs: *mut g16_r1cs);
