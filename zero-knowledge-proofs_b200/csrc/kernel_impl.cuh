@@ -10,7 +10,8 @@ namespace g16 {
 template <class F>
 void k_accumulate(stream_t s, size_t max_items, const uint32_t *pts, const uint32_t *entries, const WorkItem *work,
                   const uint32_t *n_items, uint32_t *buckets, uint32_t *chunk_out, bool add_to) {
-    launch<BucketAccumulate<F>>(max_items, s, pts, entries, work, n_items, buckets, chunk_out, add_to ? 1u : 0u);
+    if (add_to) launch<BucketAccumulate<F, true>>(max_items, s, pts, entries, work, n_items, buckets, chunk_out);
+    else launch<BucketAccumulate<F, false>>(max_items, s, pts, entries, work, n_items, buckets, chunk_out);
 }
 template <class F>
 void k_chunk_merge(stream_t s, size_t max_split, const uint32_t *split_list, const uint32_t *chunk_out, uint32_t *buckets,

@@ -382,8 +382,9 @@ G16_HD XYZZ<F> load_xyzz(const uint32_t *src, size_t idx) {
 
 // The hot kernel: one thread per work item.  Whole buckets are written straight to `buckets`; chunks of
 // split buckets go to chunk_out[item index] (split items occupy the front of the item array) and are
-// folded by ChunkMerge.  add_to != 0: the call continues an MSM whose earlier scalar chunks already left their
-// sums in `buckets` (host scalars arrive in pieces, engine.cuh) -- start from the stored sum, skip empty slices.
+// folded by ChunkMerge.  ADD_TO: the call continues an MSM whose earlier scalar chunks already left their sums in
+// `buckets` (host scalars arrive in pieces, engine.cuh) -- start from the stored sum, skip empty slices.  (A
+// compile-time flag: the one-chunk kernel is exactly the plain walk.)
 // Launch shape of the hot kernel.  Shipped values: 64 threads per block; G1 six blocks per SM (166 registers, no spill),
 // G2 left to ptxas (255 registers = 4 blocks of 64).  Measured on B200 at 2^24 (profiles/r02_run2_lab_g1_acc_launch_shape_2p24.txt):
 // 128 threads 76.1 ms, 128 x 4 blocks (128 registers) 75.3, 64 x 6 blocks 73.1, 64 x 8 blocks (128 registers) 75.8 -- the
@@ -400,17 +401,19 @@ G16_HD XYZZ<F> load_xyzz(const uint32_t *src, size_t idx) {
 #ifndef G16_ACC_MIN_BLOCKS_G2
 #define G16_ACC_MIN_BLOCKS_G2 1
 #endif
-template <class F>
+template <class F, bool ADD_TO>
 struct BucketAccumulate {
     static constexpr int BLOCK = G16_ACC_BLOCK;
     static constexpr int MIN_BLOCKS = F::N == 12 ? G16_ACC_MIN_BLOCKS_G1 : G16_ACC_MIN_BLOCKS_G2;
     G16_HD static void run(size_t t, const uint32_t *pts, const uint32_t *entries, const WorkItem *items,
-                           const uint32_t *n_items, uint32_t *buckets, uint32_t *chunk_out, uint32_t add_to) {
+                           const uint32_t *n_items, uint32_t *buckets, uint32_t *chunk_out) {
         if (t >= *n_items) return;   // the launch covers an upper bound; the exact count lives on the device
         WorkItem it = items[t];
-        const bool resume = add_to && !(it.bucket & SPLIT_FLAG);
-        if (resume && it.begin == it.end) return;
-        XYZZ<F> acc = resume ? load_xyzz<F>(buckets, it.bucket) : XYZZ<F>::inf();
+        XYZZ<F> acc = XYZZ<F>::inf();
+        if (ADD_TO && !(it.bucket & SPLIT_FLAG)) {
+            if (it.begin == it.end) return;
+            acc = load_xyzz<F>(buckets, it.bucket);
+        }
         for (uint32_t e = it.begin; e < it.end; ++e) {
             uint32_t v = entries[e];
             Affine<F> p = load_affine<F>(pts, v & 0x7fffffffu);
