@@ -401,6 +401,9 @@ G16_HD XYZZ<F> load_xyzz(const uint32_t *src, size_t idx) {
 #ifndef G16_ACC_MIN_BLOCKS_G2
 #define G16_ACC_MIN_BLOCKS_G2 1
 #endif
+#ifndef G16_ACC_PREFETCH
+#define G16_ACC_PREFETCH 0
+#endif
 template <class F, bool ADD_TO>
 struct BucketAccumulate {
     static constexpr int BLOCK = G16_ACC_BLOCK;
@@ -414,12 +417,27 @@ struct BucketAccumulate {
             if (it.begin == it.end) return;
             acc = load_xyzz<F>(buckets, it.bucket);
         }
+#if G16_ACC_PREFETCH && G16_DEVICE_CODE
+        // the point of the NEXT entry is pulled into L2 while this one is added (no registers held: a prefetch, not a load)
+        uint32_t v = it.begin < it.end ? entries[it.begin] : 0u;
+        for (uint32_t e = it.begin; e < it.end; ++e) {
+            uint32_t vn = e + 1 < it.end ? entries[e + 1] : v;
+            const uint32_t *nx = pts + (size_t)(vn & 0x7fffffffu) * (2 * F::N);
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + 2 * F::N - 1));
+            Affine<F> p = load_affine<F>(pts, v & 0x7fffffffu);
+            if (v >> 31) p.y = F::neg(p.y);
+            xyzz_madd(acc, p.x, p.y);
+            v = vn;
+        }
+#else
         for (uint32_t e = it.begin; e < it.end; ++e) {
             uint32_t v = entries[e];
             Affine<F> p = load_affine<F>(pts, v & 0x7fffffffu);
             if (v >> 31) p.y = F::neg(p.y);
             xyzz_madd(acc, p.x, p.y);
         }
+#endif
         if (it.bucket & SPLIT_FLAG) store_xyzz<F>(chunk_out, t, acc);
         else store_xyzz<F>(buckets, it.bucket, acc);
     }

@@ -25,13 +25,9 @@ def engine(*flags):
 
 
 VARIANTS = {
-    # name: {unit: [flags]}   (shipped: accumulate 64 threads x 6 blocks (G1); item floor 16; reduction split 15 / 15)
-    "item_floor8": engine("-DG16_ITEM_FLOOR=8"),
-    "item_floor32": engine("-DG16_ITEM_FLOOR=32"),
-    "red_14_15": engine("-DG16_RED_GROUPS_LOG2=14"),
-    "red_14_14": engine("-DG16_RED_GROUPS_LOG2=14", "-DG16_RED_TILE_MAX_LOG2=14"),
-    "red_16_15": engine("-DG16_RED_GROUPS_LOG2=16"),
-    "red_13_13": engine("-DG16_RED_GROUPS_LOG2=13", "-DG16_RED_TILE_MAX_LOG2=13"),
+    # name: {unit: [flags]}   (shipped: accumulate 64 threads x 6 blocks (G1), no prefetch; item floor 16; reduction split 15 / 15)
+    "g1_prefetch": {"k_acc_g1.cu": ["-DG16_ACC_PREFETCH=1"]},
+    "g2_prefetch": {"k_acc_g2.cu": ["-DG16_ACC_PREFETCH=1"]},
 }
 
 
