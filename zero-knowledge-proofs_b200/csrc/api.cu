@@ -65,9 +65,13 @@ void g16_ctx_destroy(g16_ctx *ctx) {
 #endif
         d.ws.release();
         d.timer.destroy();
+#ifndef G16_EMU
+        if (d.tail_stream) { cudaStreamSynchronize(d.tail_stream); cudaStreamDestroy(d.tail_stream); }
+#endif
         for (auto &l : d.extra) {
 #ifndef G16_EMU
             if (l->stream) cudaStreamSynchronize(l->stream);
+            if (l->tail_stream) { cudaStreamSynchronize(l->tail_stream); cudaStreamDestroy(l->tail_stream); }
 #endif
             l->ws.release();
             l->timer.destroy();
@@ -433,23 +437,28 @@ void prove_single_device(Context *c, const g16_pk *pk, const uint64_t *w, size_t
     // pi_A (lane 0), pi_B in G2 (lane 1), [H(s)]_1 (lane 2), pi_B' (lane 3), private part of pi_C (lane 4)
     size_t na = std::min(num_vars, pk->a_len), nb2 = std::min(num_vars, pk->b2_len), nb1 = std::min(num_vars, pk->b1_len);
     uint32_t *oa = LA.ws.out.as<uint32_t>(PW1 + AW1) + PW1;
-    msm_run<Fq>(LA, pk->a->shards[0], prefixed(LA, 0, 2, na), na + 2, true, co, nullptr, oa);
+#ifndef G16_PROVE_SPLIT_TAIL
+#define G16_PROVE_SPLIT_TAIL 1
+#endif
+    constexpr bool ST = G16_PROVE_SPLIT_TAIL != 0;   // tails of the five big MSMs on high-priority streams
+    constexpr size_t NP = ~(size_t)0;
+    msm_run<Fq>(LA, pk->a->shards[0], prefixed(LA, 0, 2, na), na + 2, true, co, nullptr, oa, 0, nullptr, NP, ST);
     uint32_t *ob = LB.ws.out.as<uint32_t>(PW2 + AW2) + PW2;
-    msm_run<Fq2>(LB, pk->b2->shards[0], prefixed(LB, 2, 2, nb2), nb2 + 2, true, co, nullptr, ob);
+    msm_run<Fq2>(LB, pk->b2->shards[0], prefixed(LB, 2, 2, nb2), nb2 + 2, true, co, nullptr, ob, 0, nullptr, NP, ST);
     size_t nh = (h || (dev && dev->d_h)) ? std::min(num_h, pk->h_len) : 0;
     uint32_t *oh = LH.ws.out.as<uint32_t>(PW1 + AW1) + PW1;
     if (dev && dev->d_h) {
-        msm_run<Fq>(LH, pk->h->shards[0], dev->d_h, nh, true, co, nullptr, oh);
+        msm_run<Fq>(LH, pk->h->shards[0], dev->d_h, nh, true, co, nullptr, oh, 0, nullptr, NP, ST);
     } else {
         uint32_t *d_h = LH.ws.scalars.as<uint32_t>(nh * 8 + 8);
         copy_h2d(d_h, h, nh * 32, LH.stream);
-        msm_run<Fq>(LH, pk->h->shards[0], d_h, nh, true, co, nullptr, oh);     // nh == 0 -> identity
+        msm_run<Fq>(LH, pk->h->shards[0], d_h, nh, true, co, nullptr, oh, 0, nullptr, NP, ST);     // nh == 0 -> identity
     }
     uint32_t *ob1 = LB1.ws.out.as<uint32_t>(PW1 + AW1) + PW1;
-    msm_run<Fq>(LB1, pk->b1->shards[0], prefixed(LB1, 4, 1, nb1), nb1 + 1, true, co, nullptr, ob1);
+    msm_run<Fq>(LB1, pk->b1->shards[0], prefixed(LB1, 4, 1, nb1), nb1 + 1, true, co, nullptr, ob1, 0, nullptr, NP, ST);
     size_t first_priv = pk->num_public + 1;
     size_t nic = num_vars > first_priv ? std::min(num_vars - first_priv, pk->ic_len) : 0;
-    msm_run<Fq>(LC, pk->ic->shards[0], d_w + first_priv * 8, nic, true, co, d_cparts, nullptr);
+    msm_run<Fq>(LC, pk->ic->shards[0], d_w + first_priv * 8, nic, true, co, d_cparts, nullptr, 0, nullptr, NP, ST);
     // ad-hoc part of pi_C on lane 4 once pi_A, H and pi_B' exist (device-side dependency, no host wait)
     for (Device *l : {&LA, &LH, &LB1}) stream_wait(LC.stream, l->stream);
     copy_d2d(d_adhoc_pts, oh, 96, LC.stream);

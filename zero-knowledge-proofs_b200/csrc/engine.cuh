@@ -79,6 +79,10 @@ struct Device {
     // extra lanes (own stream + workspace) on the same GPU: lets the latency-bound tail of one MSM
     // (reduction tree, inversion) overlap the bucket accumulation of another (prove schedule)
     std::vector<std::unique_ptr<Device>> extra;
+    // High-priority stream for the latency-bound tail of an MSM (bucket reduction tree, fold, inversion) when several
+    // MSMs share the GPU (prove schedule): its few, small blocks are placed ahead of the pending accumulation blocks of
+    // the other lanes instead of waiting behind their whole grids.  Created on first use.
+    stream_t tail_stream = nullptr;
 };
 
 inline void set_device(int id);
@@ -110,6 +114,18 @@ inline void set_device(int id) {
     G16_CUDA_CHECK(cudaSetDevice(id));
 #else
     (void)id;
+#endif
+}
+inline stream_t tail_stream_of(Device &dv) {
+#ifndef G16_EMU
+    if (!dv.tail_stream) {
+        int least = 0, greatest = 0;
+        G16_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        G16_CUDA_CHECK(cudaStreamCreateWithPriority(&dv.tail_stream, cudaStreamNonBlocking, greatest));
+    }
+    return dv.tail_stream;
+#else
+    return dv.stream;
 #endif
 }
 
@@ -255,7 +271,7 @@ inline void reduce_split(size_t buckets, size_t &tile_level_max, size_t &thread_
 template <class F>
 void msm_run(Device &dv, const BasesShard &sh, const uint32_t *d_scalars, size_t n, bool mont, unsigned c_override,
              uint32_t *d_out_xyzz, uint32_t *d_out_aff, size_t first = 0, const uint64_t *h_scalars = nullptr,
-             size_t pipe_min = ~(size_t)0) {
+             size_t pipe_min = ~(size_t)0, bool split_tail = false) {
     // bases [first, first + n) of the shard
     const uint32_t *pts = sh.table ? sh.table : sh.pts;
     stream_t s = dv.stream;
@@ -305,14 +321,24 @@ void msm_run(Device &dv, const BasesShard &sh, const uint32_t *d_scalars, size_t
 
     uint32_t *d_stage = const_cast<uint32_t *>(d_scalars);   // written only when the scalars come from the host
     // host scalars: all copies are queued first, back to back on the copy lane; `arrived[k]` fires when range k is in
-    event_t arrived[H2D_PIPE_PARTS] = {};
+    struct Arrivals {   // events not yet consumed are released if a launch below throws
+        event_t ev[H2D_PIPE_PARTS] = {};
+        bool live[H2D_PIPE_PARTS] = {};
+        ~Arrivals() {
+#ifndef G16_EMU
+            for (size_t k = 0; k < H2D_PIPE_PARTS; ++k)
+                if (live[k]) cudaEventDestroy(ev[k]);
+#endif
+        }
+    } arrived;
     if (h_scalars && parts > 1) {
         Device &cp = lane_of(dv, H2D_PIPE_LANE);
         stream_wait(cp.stream, s);   // earlier work on s may still read the scalar buffer
         for (size_t k = 0; k < parts; ++k) {
             size_t lo = part_lo[k], cnt = part_lo[k + 1] - lo;
             copy_h2d(d_stage + lo * 8, h_scalars + lo * 4, cnt * 32, cp.stream);
-            arrived[k] = event_record(cp.stream);
+            arrived.ev[k] = event_record(cp.stream);
+            arrived.live[k] = true;
         }
     } else if (h_scalars) {
         copy_h2d(d_stage, h_scalars, n * 32, s);
@@ -321,7 +347,10 @@ void msm_run(Device &dv, const BasesShard &sh, const uint32_t *d_scalars, size_t
     for (size_t k = 0; k < parts; ++k) {
         const size_t lo = part_lo[k], cnt = part_lo[k + 1] - lo;
         if (cnt == 0) continue;
-        if (h_scalars && parts > 1) event_wait_and_release(s, arrived[k]);
+        if (h_scalars && parts > 1) {
+            arrived.live[k] = false;
+            event_wait_and_release(s, arrived.ev[k]);
+        }
         const bool add_to = k > 0;                 // later ranges continue the bucket sums of the earlier ones
         const uint32_t *sc = d_scalars + lo * 8;
         MsmPlan pl = plan;
@@ -356,6 +385,12 @@ void msm_run(Device &dv, const BasesShard &sh, const uint32_t *d_scalars, size_t
         k_chunk_merge<F>(s, split_buckets, split_list, chunk_out, buckets, add_to, dv.sm_count);
     }
     dv.timer.mark(4, s);
+    // (prove schedule: stages 5-6 move to the lane's high-priority stream, see Device::tail_stream)
+    const stream_t main_stream = s;
+    if (split_tail) {
+        s = tail_stream_of(dv);
+        stream_wait(s, main_stream);
+    }
     // 5. parallel bucket reduction: thread levels while the level is work bound (every thread walks 2^log_l
     //    consecutive buckets), then block-cooperative levels (quad additions, scan + tree) for the latency
     //    bound top of the tree
@@ -396,6 +431,7 @@ void msm_run(Device &dv, const BasesShard &sh, const uint32_t *d_scalars, size_t
     // 6. window fold + to affine
     k_window_combine<F>(s, X, Y1, Y2, plan.bwin, plan.c, d_out_xyzz, d_out_aff);
     dv.timer.mark(6, s);
+    if (split_tail) stream_wait(main_stream, s);   // later work on the lane sees the result and may reuse the workspace
 }
 
 // Import host points (ark layout + infinity bytes) into a device shard.

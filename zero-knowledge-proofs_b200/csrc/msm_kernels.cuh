@@ -389,7 +389,8 @@ G16_HD XYZZ<F> load_xyzz(const uint32_t *src, size_t idx) {
 // G2 left to ptxas (255 registers = 4 blocks of 64).  Measured on B200 at 2^24 (profiles/r02_run2_lab_g1_acc_launch_shape_2p24.txt):
 // 128 threads 76.1 ms, 128 x 4 blocks (128 registers) 75.3, 64 x 6 blocks 73.1, 64 x 8 blocks (128 registers) 75.8 -- the
 // smaller block lets the length-sorted items of a block finish closer together.  G2 at 2^20: 16.6 ms either way, and
-// forcing three blocks of 128 (168 registers, 1.8 KB of spills) costs 22.7 ms.  tools/lab_build.py builds A/B variants of
+// forcing three blocks of 128 (168 registers, 1.8 KB of spills) costs 22.7 ms.  An L2 prefetch of the next entry's point
+// changed nothing (73.2 vs 73.1 ms, profiles/r02_run7_lab_prefetch.txt).  tools/lab_build.py builds A/B variants of
 // the library with other values (-DG16_ACC_BLOCK=.. -DG16_ACC_MIN_BLOCKS_G1=.. -DG16_ACC_MIN_BLOCKS_G2=..) for
 // tools/bench_stages.py --lib.
 #ifndef G16_ACC_BLOCK
@@ -400,9 +401,6 @@ G16_HD XYZZ<F> load_xyzz(const uint32_t *src, size_t idx) {
 #endif
 #ifndef G16_ACC_MIN_BLOCKS_G2
 #define G16_ACC_MIN_BLOCKS_G2 1
-#endif
-#ifndef G16_ACC_PREFETCH
-#define G16_ACC_PREFETCH 0
 #endif
 template <class F, bool ADD_TO>
 struct BucketAccumulate {
@@ -417,27 +415,12 @@ struct BucketAccumulate {
             if (it.begin == it.end) return;
             acc = load_xyzz<F>(buckets, it.bucket);
         }
-#if G16_ACC_PREFETCH && G16_DEVICE_CODE
-        // the point of the NEXT entry is pulled into L2 while this one is added (no registers held: a prefetch, not a load)
-        uint32_t v = it.begin < it.end ? entries[it.begin] : 0u;
-        for (uint32_t e = it.begin; e < it.end; ++e) {
-            uint32_t vn = e + 1 < it.end ? entries[e + 1] : v;
-            const uint32_t *nx = pts + (size_t)(vn & 0x7fffffffu) * (2 * F::N);
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + 2 * F::N - 1));
-            Affine<F> p = load_affine<F>(pts, v & 0x7fffffffu);
-            if (v >> 31) p.y = F::neg(p.y);
-            xyzz_madd(acc, p.x, p.y);
-            v = vn;
-        }
-#else
         for (uint32_t e = it.begin; e < it.end; ++e) {
             uint32_t v = entries[e];
             Affine<F> p = load_affine<F>(pts, v & 0x7fffffffu);
             if (v >> 31) p.y = F::neg(p.y);
             xyzz_madd(acc, p.x, p.y);
         }
-#endif
         if (it.bucket & SPLIT_FLAG) store_xyzz<F>(chunk_out, t, acc);
         else store_xyzz<F>(buckets, it.bucket, acc);
     }

@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-precompute", action="store_true")
+    ap.add_argument("--lib", default=None, help="alternative build of the library (A/B experiments, tools/lab_build.py)")
     args = ap.parse_args()
     import torch
     import bls12_381 as bls
@@ -38,7 +39,7 @@ def main():
     oracle.build()
     n = 1 << args.log_n
     dev = torch.device("cuda:0")
-    ctx = groth16_cuda.Context([0])
+    ctx = groth16_cuda.Context([0], lib_path=args.lib)
     g1 = np.array(bls.g1_to_mont(bls.G1_GEN)[0], dtype=np.uint64)
     g2 = np.array(bls.g2_to_mont(bls.G2_GEN)[0], dtype=np.uint64)
 
@@ -64,8 +65,7 @@ def main():
     t0 = time.time()
     dev_pk = ctx.pk_upload(pk)
     if not args.no_precompute:
-        ctx.lib.g16_pk_precompute.argtypes = [__import__("ctypes").c_void_p] * 2
-        ctx._check(ctx.lib.g16_pk_precompute(ctx.handle, dev_pk.handle))
+        ctx.pk_precompute(dev_pk)
     upload_s = time.time() - t0
     r = oracle.gen_scalars(0xaa, 1)[0]
     s = oracle.gen_scalars(0xbb, 1)[0]

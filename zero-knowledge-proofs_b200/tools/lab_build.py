@@ -25,9 +25,14 @@ def engine(*flags):
 
 
 VARIANTS = {
-    # name: {unit: [flags]}   (shipped: accumulate 64 threads x 6 blocks (G1), no prefetch; item floor 16; reduction split 15 / 15)
-    "g1_prefetch": {"k_acc_g1.cu": ["-DG16_ACC_PREFETCH=1"]},
-    "g2_prefetch": {"k_acc_g2.cu": ["-DG16_ACC_PREFETCH=1"]},
+    # name: {unit: [flags]}   (shipped: accumulate 64 threads x 6 blocks (G1); item floor 16; reduction split 15 / 15)
+    "g1_b128": {"k_acc_g1.cu": ["-DG16_ACC_BLOCK=128", "-DG16_ACC_MIN_BLOCKS_G1=3"]},
+    "g1_b32_mb12": {"k_acc_g1.cu": ["-DG16_ACC_BLOCK=32", "-DG16_ACC_MIN_BLOCKS_G1=12"]},
+    "g2_b128": {"k_acc_g2.cu": ["-DG16_ACC_BLOCK=128"]},
+    "prove_no_split_tail": {"api.cu": ["-DG16_PROVE_SPLIT_TAIL=0"]},
+    "item_floor8": engine("-DG16_ITEM_FLOOR=8"),
+    "red_14_15": engine("-DG16_RED_GROUPS_LOG2=14"),
+    "red_16_15": engine("-DG16_RED_GROUPS_LOG2=16"),
 }
 
 
