@@ -262,6 +262,10 @@ unsigned long long g16_launch_count(void);
  * plan = {window bits, windows, buckets per window} */
 int g16_ctx_enable_stage_timing(g16_ctx *ctx, int on);
 int g16_ctx_last_stage_ms(g16_ctx *ctx, float ms[6], unsigned plan[3]);
+/* with stage timing enabled: the timeline of the last g16_prove on a single-device ctx.  t[7 * lane + k] = ms from the
+ * start of the prove to mark k (0 start, 1 digits done, 2 items, 3 sort, 4 accumulate, 5 reduce, 6 fold) of lane
+ * 0 pi_A, 1 pi_B (G2), 2 H, 3 pi_B' (G1), 4 private part of pi_C */
+int g16_ctx_prove_timeline(g16_ctx *ctx, float t[35]);
 /* element-wise Fq ops on the device: op 0 mul, 1 add, 2 sub, 3 inverse(a), 4 square(a), 5 negate(a);
  * a, b, out: n x 6 u64 Montgomery (b may be NULL for unary ops) */
 int g16_debug_fq_op(g16_ctx *ctx, int op, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n);

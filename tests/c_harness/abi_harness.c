@@ -26,7 +26,7 @@ static fn_t table[] = {
     F(g16_prove), F(g16_quotient_h), F(g16_quotient_h_device), F(g16_r1cs_upload), F(g16_r1cs_free), F(g16_r1cs_domain_size), F(g16_r1cs_domain_evals),
     F(g16_r1cs_eval_at), F(g16_setup_crs), F(g16_prove_r1cs), F(g16_g1_serialize), F(g16_g2_serialize), F(g16_g1_deserialize),
     F(g16_g2_deserialize), F(g16_proof_serialize), F(g16_proof_deserialize), F(g16_launch_count), F(g16_ctx_enable_stage_timing),
-    F(g16_ctx_last_stage_ms), F(g16_debug_fq_op), F(g16_debug_fr_from_mont), F(g16_debug_g1_add), F(g16_debug_g2_add),
+    F(g16_ctx_last_stage_ms), F(g16_ctx_prove_timeline), F(g16_debug_fq_op), F(g16_debug_fr_from_mont), F(g16_debug_g1_add), F(g16_debug_g2_add),
 };
 
 static int run_msm(const char *path) {

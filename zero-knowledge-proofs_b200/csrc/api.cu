@@ -65,13 +65,9 @@ void g16_ctx_destroy(g16_ctx *ctx) {
 #endif
         d.ws.release();
         d.timer.destroy();
-#ifndef G16_EMU
-        if (d.tail_stream) { cudaStreamSynchronize(d.tail_stream); cudaStreamDestroy(d.tail_stream); }
-#endif
         for (auto &l : d.extra) {
 #ifndef G16_EMU
             if (l->stream) cudaStreamSynchronize(l->stream);
-            if (l->tail_stream) { cudaStreamSynchronize(l->tail_stream); cudaStreamDestroy(l->tail_stream); }
 #endif
             l->ws.release();
             l->timer.destroy();
@@ -83,6 +79,9 @@ void g16_ctx_destroy(g16_ctx *ctx) {
         if (d.own_stream && d.stream) cudaStreamDestroy(d.stream);
 #endif
     }
+#ifndef G16_EMU
+    if (ctx->c.prove_epoch) cudaEventDestroy((cudaEvent_t)ctx->c.prove_epoch);
+#endif
     delete ctx;
 }
 
@@ -391,10 +390,17 @@ void g16_pk_free(g16_pk *pk) { delete pk; }
 
 
 extern "C++" {
-// Single-device fast path of the prove schedule: the assignment is copied to the device once, every MSM
-// gets its (prefix ++ assignment) scalar vector by a device-to-device copy, the five big MSMs run on
-// five lanes, and the ad-hoc terms of pi_C (H, s*pi_A, r*pi_B') are taken from the other lanes' results
-// on the device -- the host waits exactly once, at the end.
+// Single-device fast path of the prove schedule.  The assignment is copied to the device once and every MSM gets its
+// (prefix ++ assignment) scalar vector by a device-to-device copy.  The five big MSMs live on five lanes (stream +
+// workspace each) and are ordered explicitly:
+//   1. the sort stages (digits, offsets, work items, counting sort) of ALL five run first -- they are short, and
+//      queued behind another lane's accumulation grid they would sit there for its whole duration;
+//   2. the bucket accumulations (the multiplier-bound part, each fills the GPU) run one after the other in the order
+//      pi_A, pi_B', pi_B (G2), H, private part of pi_C, chained by events;
+//   3. every lane's latency-bound tail (bucket reduction tree, fold, inversion) follows its accumulation on its own
+//      stream, i.e. under the accumulation of the next lanes; so do s * pi_A and r * pi_B' (2 ms double-and-add
+//      chains, ScalarMulAffine) -- which is why pi_A and pi_B' accumulate first;
+//   4. pi_C = private part + H + s pi_A + r pi_B' is one four-term fold on the device; the host waits once, at the end.
 void prove_single_device(Context *c, const g16_pk *pk, const uint64_t *w, size_t num_vars, const uint64_t *h,
                          size_t num_h, const uint64_t *r, const uint64_t *s, uint64_t *a_xy, uint8_t *a_inf,
                          uint64_t *b_xy, uint8_t *b_inf, uint64_t *c_xy, uint8_t *c_inf, const ProveDeviceInputs *dev) {
@@ -403,13 +409,20 @@ void prove_single_device(Context *c, const g16_pk *pk, const uint64_t *w, size_t
     set_device(d0.id);
     Device &LA = lane_of(d0, 0), &LB = lane_of(d0, 1), &LH = lane_of(d0, 2), &LB1 = lane_of(d0, 3), &LC = lane_of(d0, 4);
     unsigned co = c->c_override;
+#ifndef G16_EMU
+    if (d0.timer.enabled) {   // test hook: per-lane stage timeline of this prove (g16_ctx_prove_timeline)
+        for (Device *l : {&LB, &LH, &LB1, &LC}) { l->timer.enabled = true; l->timer.valid = false; }
+        if (!c->prove_epoch) { cudaEvent_t e; G16_CUDA_CHECK(cudaEventCreate(&e)); c->prove_epoch = e; }
+        G16_CUDA_CHECK(cudaEventRecord((cudaEvent_t)c->prove_epoch, LA.stream));
+    }
+#endif
     // small host staging block (kept alive until the final synchronisation): prefixes and ad-hoc scalars
     std::vector<uint64_t> hs(4 * 16);
     auto put = [&](size_t slot, const uint64_t *x) { memcpy(hs.data() + 4 * slot, x, 32); };
     put(0, FR_ONE_MONT); put(1, r);          // pi_A prefix   [1, r]
     put(2, FR_ONE_MONT); put(3, s);          // pi_B prefix   [1, s]
     put(4, FR_ONE_MONT);                     // pi_B' prefix  [1]
-    put(5, FR_ONE_MONT); put(6, s); put(7, r);   // ad-hoc terms of pi_C: [1 * H, s * pi_A, r * pi_B']
+    put(6, s); put(7, r);                    // multipliers of pi_A and pi_B' inside pi_C
 
     // assignment: one H2D, shared by four MSMs
     // (or already on the device, produced on lane 0's stream by the R1CS path)
@@ -419,11 +432,10 @@ void prove_single_device(Context *c, const g16_pk *pk, const uint64_t *w, size_t
         copy_h2d(buf, w, num_vars * 32, LA.stream);
         d_w = buf;
     }
-    uint32_t *d_misc = LA.ws.prove_misc.as<uint32_t>(16 * 8 + 3 * 24 + 2 * PW1 + AW1 + 64);
+    uint32_t *d_misc = LA.ws.prove_misc.as<uint32_t>(16 * 8 + 4 * PW1 + AW1 + 64);
     uint32_t *d_small = d_misc;                       // 16 scalars
-    uint32_t *d_adhoc_pts = d_misc + 16 * 8;          // 3 packed G1 points
-    uint32_t *d_cparts = d_adhoc_pts + 3 * 24;        // 2 projective partials of pi_C
-    uint32_t *d_c_aff = d_cparts + 2 * PW1;           // pi_C affine
+    uint32_t *d_cparts = d_misc + 16 * 8;             // 4 projective terms of pi_C: private part, H, s pi_A, r pi_B'
+    uint32_t *d_c_aff = d_cparts + 4 * PW1;           // pi_C affine
     copy_h2d(d_small, hs.data(), 16 * 32, LA.stream);
     for (Device *l : {&LB, &LB1, &LC}) stream_wait(l->stream, LA.stream);
     if (dev) stream_wait(LH.stream, LA.stream);
@@ -432,42 +444,59 @@ void prove_single_device(Context *c, const g16_pk *pk, const uint64_t *w, size_t
         uint32_t *d = L.ws.scalars.as<uint32_t>((k + n) * 8 + 8);
         copy_d2d(d, d_small + slot * 8, k * 32, L.stream);
         copy_d2d(d + k * 8, d_w, n * 32, L.stream);
-        return d;
+        return (const uint32_t *)d;
     };
-    // pi_A (lane 0), pi_B in G2 (lane 1), [H(s)]_1 (lane 2), pi_B' (lane 3), private part of pi_C (lane 4)
     size_t na = std::min(num_vars, pk->a_len), nb2 = std::min(num_vars, pk->b2_len), nb1 = std::min(num_vars, pk->b1_len);
-    uint32_t *oa = LA.ws.out.as<uint32_t>(PW1 + AW1) + PW1;
-#ifndef G16_PROVE_SPLIT_TAIL
-#define G16_PROVE_SPLIT_TAIL 1
-#endif
-    constexpr bool ST = G16_PROVE_SPLIT_TAIL != 0;   // tails of the five big MSMs on high-priority streams
-    constexpr size_t NP = ~(size_t)0;
-    msm_run<Fq>(LA, pk->a->shards[0], prefixed(LA, 0, 2, na), na + 2, true, co, nullptr, oa, 0, nullptr, NP, ST);
-    uint32_t *ob = LB.ws.out.as<uint32_t>(PW2 + AW2) + PW2;
-    msm_run<Fq2>(LB, pk->b2->shards[0], prefixed(LB, 2, 2, nb2), nb2 + 2, true, co, nullptr, ob, 0, nullptr, NP, ST);
     size_t nh = (h || (dev && dev->d_h)) ? std::min(num_h, pk->h_len) : 0;
-    uint32_t *oh = LH.ws.out.as<uint32_t>(PW1 + AW1) + PW1;
-    if (dev && dev->d_h) {
-        msm_run<Fq>(LH, pk->h->shards[0], dev->d_h, nh, true, co, nullptr, oh, 0, nullptr, NP, ST);
-    } else {
-        uint32_t *d_h = LH.ws.scalars.as<uint32_t>(nh * 8 + 8);
-        copy_h2d(d_h, h, nh * 32, LH.stream);
-        msm_run<Fq>(LH, pk->h->shards[0], d_h, nh, true, co, nullptr, oh, 0, nullptr, NP, ST);     // nh == 0 -> identity
-    }
-    uint32_t *ob1 = LB1.ws.out.as<uint32_t>(PW1 + AW1) + PW1;
-    msm_run<Fq>(LB1, pk->b1->shards[0], prefixed(LB1, 4, 1, nb1), nb1 + 1, true, co, nullptr, ob1, 0, nullptr, NP, ST);
     size_t first_priv = pk->num_public + 1;
     size_t nic = num_vars > first_priv ? std::min(num_vars - first_priv, pk->ic_len) : 0;
-    msm_run<Fq>(LC, pk->ic->shards[0], d_w + first_priv * 8, nic, true, co, d_cparts, nullptr, 0, nullptr, NP, ST);
-    // ad-hoc part of pi_C on lane 4 once pi_A, H and pi_B' exist (device-side dependency, no host wait)
+    const uint32_t *sc_a = prefixed(LA, 0, 2, na), *sc_b2 = prefixed(LB, 2, 2, nb2), *sc_b1 = prefixed(LB1, 4, 1, nb1);
+    const uint32_t *sc_h = dev ? dev->d_h : nullptr;
+    if (nh && !sc_h) {
+        uint32_t *d_h = LH.ws.scalars.as<uint32_t>(nh * 8 + 8);
+        copy_h2d(d_h, h, nh * 32, LH.stream);
+        sc_h = d_h;
+    }
+    uint32_t *oa = LA.ws.out.as<uint32_t>(PW1 + AW1) + PW1;      // pi_A affine
+    uint32_t *ob = LB.ws.out.as<uint32_t>(PW2 + AW2) + PW2;      // pi_B affine (G2)
+    uint32_t *ob1 = LB1.ws.out.as<uint32_t>(PW1 + AW1) + PW1;    // pi_B' affine
+    uint32_t *t_priv = d_cparts, *t_h = d_cparts + PW1, *t_sa = d_cparts + 2 * PW1, *t_rb1 = d_cparts + 3 * PW1;
+
+    // the five MSMs in accumulation order; an empty one (no H coefficients, no private variables) contributes the identity
+    MsmJob<Fq> ja(LA, pk->a->shards[0], na + 2, co, 0), jb1(LB1, pk->b1->shards[0], nb1 + 1, co, 0);
+    MsmJob<Fq2> jb2(LB, pk->b2->shards[0], nb2 + 2, co, 0);
+    std::unique_ptr<MsmJob<Fq>> jh(nh ? new MsmJob<Fq>(LH, pk->h->shards[0], nh, co, 0) : nullptr);
+    std::unique_ptr<MsmJob<Fq>> jc(nic ? new MsmJob<Fq>(LC, pk->ic->shards[0], nic, co, 0) : nullptr);
+    // 1. sort stages of all lanes
+    ja.front(sc_a, 0, na + 2, true, true);
+    jb1.front(sc_b1, 0, nb1 + 1, true, true);
+    jb2.front(sc_b2, 0, nb2 + 2, true, true);
+    if (jh) jh->front(sc_h, 0, nh, true, true);
+    if (jc) jc->front(d_w + first_priv * 8, 0, nic, true, true);
+    // 2. + 3. accumulations one after the other, every tail right behind its accumulation on its own stream
+    event_t done = nullptr;
+    bool have = false;
+    auto gate = [&](Device &L) {            // this lane's accumulation starts when the previous one has finished
+        if (have) event_wait_and_release(L.stream, done);
+        have = false;
+    };
+    auto passed = [&](Device &L) { done = event_record(L.stream); have = true; };
+    gate(LA); ja.accumulate(false); passed(LA);
+    ja.back(nullptr, oa);
+    k_scalar_mul_affine<Fq>(LA.stream, 1, d_small + 6 * 8, oa, (uint32_t)AW1, t_sa);
+    gate(LB1); jb1.accumulate(false); passed(LB1);
+    jb1.back(nullptr, ob1);
+    k_scalar_mul_affine<Fq>(LB1.stream, 1, d_small + 7 * 8, ob1, (uint32_t)AW1, t_rb1);
+    gate(LB); jb2.accumulate(false); passed(LB);
+    jb2.back(nullptr, ob);
+    if (jh) { gate(LH); jh->accumulate(false); passed(LH); jh->back(t_h, nullptr); }
+    else k_partial_combine<Fq>(LH.stream, nullptr, 0u, t_h, nullptr);
+    if (jc) { gate(LC); jc->accumulate(false); passed(LC); jc->back(t_priv, nullptr); }
+    else k_partial_combine<Fq>(LC.stream, nullptr, 0u, t_priv, nullptr);
+    if (have) { event_wait_and_release(LC.stream, done); have = false; }
+    // 4. pi_C on lane 4 once the other three terms exist (device-side dependency, no host wait)
     for (Device *l : {&LA, &LH, &LB1}) stream_wait(LC.stream, l->stream);
-    copy_d2d(d_adhoc_pts, oh, 96, LC.stream);
-    copy_d2d(d_adhoc_pts + 24, oa, 96, LC.stream);
-    copy_d2d(d_adhoc_pts + 48, ob1, 96, LC.stream);
-    BasesShard adhoc;
-    adhoc.dev = 0; adhoc.cuda_dev = d0.id; adhoc.pts = d_adhoc_pts; adhoc.n = 3; adhoc.owned = false;
-    msm_run<Fq>(LC, adhoc, d_small + 5 * 8, 3, true, 0, d_cparts + PW1, nullptr);
-    k_partial_combine<Fq>(LC.stream, d_cparts, 2, nullptr, d_c_aff);
+    k_partial_combine<Fq>(LC.stream, d_cparts, 4, nullptr, d_c_aff);
 
     uint32_t ra[AW1], rb[AW2], rc[AW1];
     copy_d2h(ra, oa, AW1 * 4, LA.stream);
@@ -497,7 +526,7 @@ void prove_multi_device(Context *c, const g16_pk *pk, const uint64_t *w, size_t 
     put(0, FR_ONE_MONT); put(1, r);              // pi_A prefix   [1, r]
     put(2, FR_ONE_MONT); put(3, s);              // pi_B prefix   [1, s]
     put(4, FR_ONE_MONT);                         // pi_B' prefix  [1]
-    put(5, FR_ONE_MONT); put(6, s); put(7, r);   // ad-hoc terms of pi_C: [1 * H, s * pi_A, r * pi_B']
+    put(6, s); put(7, r);                        // multipliers of pi_A and pi_B' inside pi_C
 
     const size_t first_priv = pk->num_public + 1;
     struct Job { const Bases *bases; size_t prefix, slot, n_src, src_off; int lane; bool g2, from_h; };
@@ -575,27 +604,24 @@ void prove_multi_device(Context *c, const g16_pk *pk, const uint64_t *w, size_t 
         }
     set_device(d0.id);
     uint32_t *aff = parts + 5 * (G + 1) * PW2;               // A, B (G2), H, B' affine results, AW2 words apart
-    uint32_t *oa = aff, *ob = aff + AW2, *oh = aff + 2 * AW2, *ob1 = aff + 3 * AW2;
-    uint32_t *d_adhoc_pts = aff + 4 * AW2;                   // 3 packed G1 points
+    uint32_t *oa = aff, *ob = aff + AW2, *ob1 = aff + 3 * AW2;
     auto fold_g1 = [&](int job, uint32_t *out_aff) {
         // G1 partials sit PW2 words apart: compact them in place before the fold (slot 0 stays)
         for (size_t k = 1; k < G; ++k) copy_d2d(part_of(job, 0) + k * PW1, part_of(job, k), PW1 * 4, LC0.stream);
         k_partial_combine<Fq>(LC0.stream, part_of(job, 0), (uint32_t)G, nullptr, out_aff);
     };
     fold_g1(0, oa);
-    k_partial_combine<Fq2>(LC0.stream, part_of(1, 0), (uint32_t)G, nullptr, ob);
-    fold_g1(2, oh);
     fold_g1(3, ob1);
-    copy_d2d(d_adhoc_pts, oh, 96, LC0.stream);
-    copy_d2d(d_adhoc_pts + 24, oa, 96, LC0.stream);
-    copy_d2d(d_adhoc_pts + 48, ob1, 96, LC0.stream);
-    for (size_t k = 1; k < G; ++k) copy_d2d(part_of(4, 0) + k * PW1, part_of(4, k), PW1 * 4, LC0.stream);
-    BasesShard adhoc;
-    adhoc.dev = 0; adhoc.cuda_dev = d0.id; adhoc.pts = d_adhoc_pts; adhoc.n = 3; adhoc.owned = false;
+    // s * pi_A and r * pi_B' (one launch, two chains side by side in one warp), then the G2 fold and the H fold
+    uint32_t *terms = part_of(4, 0);                          // [private part x G | H | s pi_A | r pi_B']
     const uint32_t *d_small0 = (const uint32_t *)lane_of(d0, 0).ws.prove_misc.p;
-    msm_run<Fq>(LC0, adhoc, d_small0 + 5 * 8, 3, true, 0, part_of(4, 0) + G * PW1, nullptr);
-    uint32_t *d_c_aff = d_adhoc_pts + 3 * 24;
-    k_partial_combine<Fq>(LC0.stream, part_of(4, 0), (uint32_t)G + 1, nullptr, d_c_aff);
+    for (size_t k = 1; k < G; ++k) copy_d2d(terms + k * PW1, part_of(4, k), PW1 * 4, LC0.stream);
+    k_scalar_mul_affine<Fq>(LC0.stream, 2, d_small0 + 6 * 8, oa, (uint32_t)(3 * AW2), terms + (G + 1) * PW1);
+    k_partial_combine<Fq2>(LC0.stream, part_of(1, 0), (uint32_t)G, nullptr, ob);
+    for (size_t k = 1; k < G; ++k) copy_d2d(part_of(2, 0) + k * PW1, part_of(2, k), PW1 * 4, LC0.stream);
+    k_partial_combine<Fq>(LC0.stream, part_of(2, 0), (uint32_t)G, terms + G * PW1, nullptr);
+    uint32_t *d_c_aff = aff + 4 * AW2;
+    k_partial_combine<Fq>(LC0.stream, terms, (uint32_t)G + 3, nullptr, d_c_aff);
 
     uint32_t ra[AW1], rb[AW2], rc[AW1];
     copy_d2h(ra, oa, AW1 * 4, LC0.stream);
@@ -665,7 +691,10 @@ unsigned long long g16_launch_count(void) { return launch_count(); }
 
 int g16_ctx_enable_stage_timing(g16_ctx *ctx, int on) {
     if (!ctx) return G16_ERR_INVALID;
-    for (auto &d : ctx->c.devs) { d.timer.enabled = on != 0; d.timer.valid = false; }
+    for (auto &d : ctx->c.devs) {
+        d.timer.enabled = on != 0; d.timer.valid = false;
+        for (auto &l : d.extra) { l->timer.enabled = false; l->timer.valid = false; }   // lanes: switched on per prove
+    }
     return G16_OK;
 }
 int g16_ctx_last_stage_ms(g16_ctx *ctx, float ms[6], unsigned plan[3]) {
@@ -678,6 +707,17 @@ int g16_ctx_last_stage_ms(g16_ctx *ctx, float ms[6], unsigned plan[3]) {
     });
 }
 
+int g16_ctx_prove_timeline(g16_ctx *ctx, float t[35]) {
+    if (!ctx || !t) return G16_ERR_INVALID;
+    return guarded(ctx, [&] {
+        Device &d0 = single_device(ctx);
+        for (int lane = 0; lane < 5; ++lane) {
+            Device &l = lane_of(d0, lane);
+            stream_sync(l.stream);
+            require(l.timer.read_since(ctx->c.prove_epoch, t + 7 * lane), "no timed prove has run (g16_ctx_enable_stage_timing)");
+        }
+    });
+}
 int g16_debug_fq_op(g16_ctx *ctx, int op, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n) {
     if (!ctx) return G16_ERR_INVALID;
     return guarded(ctx, [&] {

@@ -50,6 +50,16 @@ struct StageTimer {
         (void)i; (void)s;
 #endif
     }
+    // elapsed ms from `epoch` (an event recorded earlier on any stream of the device) to every mark
+    bool read_since(void *epoch, float *t) {
+#ifndef G16_EMU
+        if (!enabled || !valid || !epoch) return false;
+        for (int i = 0; i <= N_STAGES; ++i) G16_CUDA_CHECK(cudaEventElapsedTime(&t[i], (cudaEvent_t)epoch, ev[i]));
+        return true;
+#else
+        (void)epoch; (void)t; return false;
+#endif
+    }
     // call after the stream has been synchronised
     bool read(float *ms) {
 #ifndef G16_EMU
@@ -79,10 +89,6 @@ struct Device {
     // extra lanes (own stream + workspace) on the same GPU: lets the latency-bound tail of one MSM
     // (reduction tree, inversion) overlap the bucket accumulation of another (prove schedule)
     std::vector<std::unique_ptr<Device>> extra;
-    // High-priority stream for the latency-bound tail of an MSM (bucket reduction tree, fold, inversion) when several
-    // MSMs share the GPU (prove schedule): its few, small blocks are placed ahead of the pending accumulation blocks of
-    // the other lanes instead of waiting behind their whole grids.  Created on first use.
-    stream_t tail_stream = nullptr;
 };
 
 inline void set_device(int id);
@@ -116,19 +122,6 @@ inline void set_device(int id) {
     (void)id;
 #endif
 }
-inline stream_t tail_stream_of(Device &dv) {
-#ifndef G16_EMU
-    if (!dv.tail_stream) {
-        int least = 0, greatest = 0;
-        G16_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
-        G16_CUDA_CHECK(cudaStreamCreateWithPriority(&dv.tail_stream, cudaStreamNonBlocking, greatest));
-    }
-    return dv.tail_stream;
-#else
-    return dv.stream;
-#endif
-}
-
 // Host-scalar MSMs of at least `h2d_pipe_min` scalars are cut into H2D_PIPE_PARTS index ranges of growing size
 // (1/32, 5/32, 26/32 of the scalars).  The ranges are copied back to back on a second stream; each one is decomposed,
 // sorted and accumulated INTO THE SAME bucket array as soon as it has arrived, and the buckets are reduced once at the
@@ -145,6 +138,7 @@ constexpr int H2D_PIPE_LANE = 7;   // lanes 0-4: prove schedule
 struct Context {
     std::vector<Device> devs;
     std::string err;
+    void *prove_epoch = nullptr;   // cudaEvent_t recorded at the start of the last timed prove (test hook: lane timeline)
     unsigned c_override = 0;
     size_t h2d_pipe_min = H2D_PIPE_MIN;
 };
@@ -261,8 +255,145 @@ inline void reduce_split(size_t buckets, size_t &tile_level_max, size_t &thread_
     tile_level_max = (size_t)1 << (big ? 16 : G16_RED_TILE_MAX_LOG2);
 }
 
+// One MSM on one lane as three steps, so that a schedule of several MSMs (prove) can order them: `front` = stages 1-3
+// (digits, bucket offsets + work items, counting sort) for a range of the scalars, `accumulate` = stage 4 for that
+// range (the hot kernel), `back` = stages 5-6 (bucket reduction, fold, to affine).  All asynchronous on dv.stream.
+template <class F>
+struct MsmJob {
+    Device &dv;
+    const uint32_t *pts = nullptr;   // resident bases (or their table of multiples)
+    MsmPlan plan{};
+    size_t n = 0, first = 0, n_max = 0, total = 0, nbins = 0;
+    uint32_t *counts = nullptr, *codes = nullptr, *ranks = nullptr, *scan_tmp = nullptr, *bins = nullptr, *bin_cursor = nullptr;
+    uint32_t *split_list = nullptr, *entries = nullptr, *staging = nullptr, *part_cursor = nullptr, *buckets = nullptr, *chunk_out = nullptr;
+    WorkItem *items = nullptr;
+    uint32_t item_max = 0;      // of the range `front` handled last
+    size_t n_entries = 0;
+
+    // bases [first_, first_ + n_) of the shard; ranges of at most n_max_ scalars will be fed (0 = the whole call at once).
+    // Takes every workspace buffer before anything is queued (growing a buffer frees the old one).
+    MsmJob(Device &dv_, const BasesShard &sh, size_t n_, unsigned c_override, size_t first_, size_t n_max_ = 0) : dv(dv_) {
+        n = n_; first = first_; n_max = n_max_ ? n_max_ : n_;
+        pts = sh.table ? sh.table : sh.pts;
+        if (n >= (1ull << 31)) throw Error{G16_ERR_INVALID, "MSM length must be < 2^31"};
+        plan = sh.table ? make_shared_plan(sh.pre_c, sh.n) : make_plan(n, c_override, 2 * FieldWords<F>::N);
+        total = plan.total;
+        if ((double)n * plan.nwin >= 4294967295.0) throw Error{G16_ERR_INVALID, "n * windows exceeds 2^32 entries"};
+        plan.offset = (uint32_t)first;
+        dv.last_plan = plan;
+        Workspace &ws = dv.ws;
+        const size_t max_entries = n_max * plan.nwin;
+        nbins = k_item_bins();
+        counts = ws.counts.as<uint32_t>(total + 1);
+        codes = ws.codes.as<uint32_t>(max_entries);
+        ranks = ws.ranks.as<uint32_t>(max_entries);
+        scan_tmp = ws.scan_tmp.as<uint32_t>(k_scan_tmp_words(total + 1));
+        bins = ws.bins.as<uint32_t>(2 * (nbins + 1));
+        bin_cursor = bins + nbins + 1;
+        const size_t item_min = std::min<size_t>(k_item_max(), ITEM_FLOOR);
+        const size_t max_split_buckets = max_entries / item_min + 1;     // buckets longer than the shortest item limit
+        const size_t max_split = 2 * max_split_buckets + 16;             // chunks they are cut into
+        items = (WorkItem *)ws.items.need((total + max_split) * k_item_bytes());
+        split_list = ws.item_start.as<uint32_t>(1 + 3 * max_split_buckets);
+        entries = ws.entries.as<uint32_t>(max_entries);
+        if (max_entries * 4 > SCATTER_TWO_PASS_BYTES) {
+            staging = ws.scatter_stage.as<uint32_t>(2 * max_entries + 2);
+            part_cursor = ws.cursor.as<uint32_t>((max_entries >> k_scatter_log_part(max_entries)) + 2);
+        }
+        buckets = ws.buckets.as<uint32_t>(total * 4 * FieldWords<F>::N);
+        chunk_out = ws.chunk_out.as<uint32_t>(max_split * 4 * FieldWords<F>::N);
+    }
+
+    // stages 1-3 for scalars [lo, lo + cnt) of the call; sc points at the first of them (device)
+    void front(const uint32_t *sc, size_t lo, size_t cnt, bool mont, bool timed) {
+        stream_t s = dv.stream;
+        MsmPlan pl = plan;
+        pl.offset = (uint32_t)(first + lo);
+        n_entries = cnt * plan.nwin;
+        if (timed) dv.timer.mark(0, s);
+        // 1. canonical scalars -> signed digits: bucket histogram + per-window code array; the histogram atomic also
+        //    hands out the digit's rank inside its bucket
+        dev_memset(counts, 0, (total + 1) * sizeof(uint32_t), s);
+        k_digit_decompose(s, cnt, sc, mont, pl, counts, codes, ranks);
+        if (timed) dv.timer.mark(1, s);
+        // 2. bucket offsets (exclusive scan; offsets[total] = number of entries) and the work-item list (bucket slices
+        //    ordered by length, longest first).  Longest item: 256 additions when the range is large, shorter when it
+        //    is small and the longest item would set the kernel's duration
+        k_exclusive_scan(s, counts, counts, total + 1, scan_tmp);
+        uint32_t *offsets = counts;
+        item_max = (uint32_t)std::min<size_t>(k_item_max(), std::max<size_t>(ITEM_FLOOR, n_entries >> ITEM_SHIFT));
+        dev_memset(bins, 0, (nbins + 1) * sizeof(uint32_t), s);
+        k_item_count(s, total, offsets, item_max, bins);
+        k_exclusive_scan(s, bins, bins, nbins + 1, scan_tmp);
+        copy_d2d(bin_cursor, bins, (nbins + 1) * sizeof(uint32_t), s);
+        dev_memset(split_list, 0, sizeof(uint32_t), s);
+        k_item_scatter(s, total, offsets, item_max, bin_cursor, items, split_list);
+        if (timed) dv.timer.mark(2, s);
+        // 3. counting-sort scatter of (point index, sign) into bucket order: position = bucket offset + rank.  Entry
+        //    arrays beyond L2 go through the two-pass partitioned scatter (msm_kernels.cuh)
+        if (n_entries * 4 > SCATTER_TWO_PASS_BYTES) k_scatter_partitioned(s, cnt, codes, ranks, pl, offsets, n_entries, part_cursor, staging, entries);
+        else k_scatter_ranked(s, cnt, codes, ranks, pl, offsets, entries);
+        if (timed) dv.timer.mark(3, s);
+    }
+
+    // stage 4 for the range `front` handled last: bucket accumulation (the hot kernel) + fold of split buckets.
+    // add_to: continue the bucket sums earlier ranges of the same call left behind
+    void accumulate(bool add_to) {
+        stream_t s = dv.stream;
+        size_t split_buckets = n_entries / item_max + 1, split_items = 2 * split_buckets + 16;
+        k_accumulate<F>(s, total + split_items, pts, entries, items, bins + nbins, buckets, chunk_out, add_to);
+        k_chunk_merge<F>(s, split_buckets, split_list, chunk_out, buckets, add_to, dv.sm_count);
+    }
+
+    // stages 5-6.  d_out_xyzz: 4 * FieldWords<F>::N words (may be null), d_out_aff: 2 * FieldWords<F>::N + 1 words (may be null)
+    void back(uint32_t *d_out_xyzz, uint32_t *d_out_aff) {
+        stream_t s = dv.stream;
+        Workspace &ws = dv.ws;
+        dv.timer.mark(4, s);
+        // 5. parallel bucket reduction: thread levels while the level is work bound (every thread walks 2^log_l
+        //    consecutive buckets), then block-cooperative levels (quad additions, scan + tree) for the latency
+        //    bound top of the tree
+        const uint32_t *X = buckets, *Y1 = nullptr, *Y2 = nullptr;
+        uint32_t n_in = plan.nb, shift = 0;
+        int flip = 0;
+        constexpr size_t PWORDS = 4 * FieldWords<F>::N;
+        size_t TILE_LEVEL_MAX, THREAD_LEVEL_GROUPS;
+        reduce_split((size_t)plan.bwin * plan.nb, TILE_LEVEL_MAX, THREAD_LEVEL_GROUPS);
+        while (n_in > 1) {
+            uint32_t n_out, log_l;
+            if ((size_t)plan.bwin * n_in > TILE_LEVEL_MAX) {
+                // aim at ~2^15 groups: fewer and the serial walk (2 x 2^log_l dependent additions) is latency
+                // bound, more and the tile levels above get more blocks than one wave
+                log_l = 2;
+                while (log_l < REDUCE_LOG_L && ((size_t)plan.bwin * n_in >> log_l) > THREAD_LEVEL_GROUPS) ++log_l;
+                uint32_t L = 1u << log_l;
+                n_out = (n_in + L - 1) / L;
+                uint32_t *Xo = ws.red[flip].as<uint32_t>((size_t)plan.bwin * n_out * PWORDS);
+                uint32_t *Yo = ws.red[flip + 1].as<uint32_t>((size_t)plan.bwin * n_out * PWORDS);
+                k_reduce_level<F>(s, (size_t)plan.bwin * n_out, X, Y1, n_in, n_out, L, shift, Xo, Yo);
+                X = Xo; Y1 = Yo;
+            } else {
+                uint32_t tile_max = k_tile_entries();
+                log_l = 1;
+                while ((1u << log_l) < n_in && (1u << log_l) < tile_max) ++log_l;
+                uint32_t T = 1u << log_l;
+                n_out = (n_in + T - 1) / T;
+                uint32_t *Xo = ws.red[flip].as<uint32_t>((size_t)plan.bwin * n_out * PWORDS);
+                uint32_t *Y1o = ws.red[flip + 1].as<uint32_t>((size_t)plan.bwin * n_out * PWORDS);
+                uint32_t *Y2o = (Y1 || Y2) ? ws.red[flip + 2].as<uint32_t>((size_t)plan.bwin * n_out * PWORDS) : nullptr;
+                k_tile_reduce<F>(s, plan.bwin, X, Y1, Y2, n_in, n_out, T, shift, Xo, Y1o, Y2o);
+                X = Xo; Y1 = Y1o; Y2 = Y2o;
+            }
+            n_in = n_out; shift += log_l; flip ^= 3;
+        }
+        dv.timer.mark(5, s);
+        // 6. window fold + to affine
+        k_window_combine<F>(s, X, Y1, Y2, plan.bwin, plan.c, d_out_xyzz, d_out_aff);
+        dv.timer.mark(6, s);
+    }
+};
+
 // One MSM on one device, asynchronous on dv.stream.
-//   pts        : packed affine bases on this device (n points)
 //   d_scalars  : n x 8 u32 on this device
 //   d_out_xyzz : 4*FieldWords<F>::N words (may be null), d_out_aff : 2*FieldWords<F>::N + 1 words (may be null)
 // h_scalars (optional): the scalars still live on the host and are copied into d_scalars here.  From pipe_min scalars
@@ -271,22 +402,12 @@ inline void reduce_split(size_t buckets, size_t &tile_level_max, size_t &thread_
 template <class F>
 void msm_run(Device &dv, const BasesShard &sh, const uint32_t *d_scalars, size_t n, bool mont, unsigned c_override,
              uint32_t *d_out_xyzz, uint32_t *d_out_aff, size_t first = 0, const uint64_t *h_scalars = nullptr,
-             size_t pipe_min = ~(size_t)0, bool split_tail = false) {
-    // bases [first, first + n) of the shard
-    const uint32_t *pts = sh.table ? sh.table : sh.pts;
+             size_t pipe_min = ~(size_t)0) {
     stream_t s = dv.stream;
-    Workspace &ws = dv.ws;
     if (n == 0) {
         k_partial_combine<F>(s, nullptr, 0u, d_out_xyzz, d_out_aff);
         return;
     }
-    if (n >= (1ull << 31)) throw Error{G16_ERR_INVALID, "MSM length must be < 2^31"};
-    MsmPlan plan = sh.table ? make_shared_plan(sh.pre_c, sh.n) : make_plan(n, c_override, 2 * FieldWords<F>::N);
-    size_t total = plan.total;
-    if ((double)n * plan.nwin >= 4294967295.0) throw Error{G16_ERR_INVALID, "n * windows exceeds 2^32 entries"};
-    plan.offset = (uint32_t)first;
-    dv.last_plan = plan;
-
     // index ranges of the scalars that run stages 1-4 one after the other (one range unless the H2D copy is pipelined)
     size_t part_lo[H2D_PIPE_PARTS + 1] = {0, n, n, n}, parts = 1;
     if (h_scalars && n >= pipe_min && n >= 64) {
@@ -296,28 +417,7 @@ void msm_run(Device &dv, const BasesShard &sh, const uint32_t *d_scalars, size_t
     }
     size_t n_max = 0;
     for (size_t k = 0; k < parts; ++k) n_max = std::max(n_max, part_lo[k + 1] - part_lo[k]);
-
-    // workspaces sized for the largest range, taken before anything is queued (growing a buffer frees the old one)
-    const size_t max_entries = n_max * plan.nwin;
-    const size_t nbins = k_item_bins();
-    uint32_t *counts = ws.counts.as<uint32_t>(total + 1);
-    uint32_t *codes = ws.codes.as<uint32_t>(max_entries);
-    uint32_t *ranks = ws.ranks.as<uint32_t>(max_entries);
-    uint32_t *scan_tmp = ws.scan_tmp.as<uint32_t>(k_scan_tmp_words(total + 1));
-    uint32_t *bins = ws.bins.as<uint32_t>(2 * (nbins + 1));
-    uint32_t *bin_cursor = bins + nbins + 1;
-    const size_t item_min = std::min<size_t>(k_item_max(), ITEM_FLOOR);
-    const size_t max_split_buckets = max_entries / item_min + 1;     // buckets longer than the shortest item limit
-    const size_t max_split = 2 * max_split_buckets + 16;             // chunks they are cut into
-    const size_t max_items = total + max_split;
-    WorkItem *items = (WorkItem *)ws.items.need(max_items * k_item_bytes());
-    uint32_t *split_list = ws.item_start.as<uint32_t>(1 + 3 * max_split_buckets);
-    uint32_t *entries = ws.entries.as<uint32_t>(max_entries);
-    const bool two_pass = max_entries * 4 > SCATTER_TWO_PASS_BYTES;
-    uint32_t *staging = two_pass ? ws.scatter_stage.as<uint32_t>(2 * max_entries + 2) : nullptr;
-    uint32_t *part_cursor = two_pass ? ws.cursor.as<uint32_t>((max_entries >> k_scatter_log_part(max_entries)) + 2) : nullptr;
-    uint32_t *buckets = ws.buckets.as<uint32_t>(total * 4 * FieldWords<F>::N);
-    uint32_t *chunk_out = ws.chunk_out.as<uint32_t>(max_split * 4 * FieldWords<F>::N);
+    MsmJob<F> job(dv, sh, n, c_override, first, n_max);
 
     uint32_t *d_stage = const_cast<uint32_t *>(d_scalars);   // written only when the scalars come from the host
     // host scalars: all copies are queued first, back to back on the copy lane; `arrived[k]` fires when range k is in
@@ -343,7 +443,6 @@ void msm_run(Device &dv, const BasesShard &sh, const uint32_t *d_scalars, size_t
     } else if (h_scalars) {
         copy_h2d(d_stage, h_scalars, n * 32, s);
     }
-
     for (size_t k = 0; k < parts; ++k) {
         const size_t lo = part_lo[k], cnt = part_lo[k + 1] - lo;
         if (cnt == 0) continue;
@@ -351,87 +450,10 @@ void msm_run(Device &dv, const BasesShard &sh, const uint32_t *d_scalars, size_t
             arrived.live[k] = false;
             event_wait_and_release(s, arrived.ev[k]);
         }
-        const bool add_to = k > 0;                 // later ranges continue the bucket sums of the earlier ones
-        const uint32_t *sc = d_scalars + lo * 8;
-        MsmPlan pl = plan;
-        pl.offset = (uint32_t)(first + lo);
-        const size_t n_entries = cnt * plan.nwin;
-        if (k == 0) dv.timer.mark(0, s);
-        // 1. canonical scalars -> signed digits: bucket histogram + per-window code array; the histogram atomic also
-        //    hands out the digit's rank inside its bucket
-        dev_memset(counts, 0, (total + 1) * sizeof(uint32_t), s);
-        k_digit_decompose(s, cnt, sc, mont, pl, counts, codes, ranks);
-        if (k == 0) dv.timer.mark(1, s);
-        // 2. bucket offsets (exclusive scan; offsets[total] = number of entries) and the work-item list
-        //    (bucket slices ordered by length, longest first)
-        k_exclusive_scan(s, counts, counts, total + 1, scan_tmp);
-        uint32_t *offsets = counts;
-        uint32_t item_max = (uint32_t)std::min<size_t>(k_item_max(), std::max<size_t>(ITEM_FLOOR, n_entries >> ITEM_SHIFT));
-        dev_memset(bins, 0, (nbins + 1) * sizeof(uint32_t), s);
-        k_item_count(s, total, offsets, item_max, bins);
-        k_exclusive_scan(s, bins, bins, nbins + 1, scan_tmp);
-        copy_d2d(bin_cursor, bins, (nbins + 1) * sizeof(uint32_t), s);
-        dev_memset(split_list, 0, sizeof(uint32_t), s);
-        k_item_scatter(s, total, offsets, item_max, bin_cursor, items, split_list);
-        if (k == 0) dv.timer.mark(2, s);
-        // 3. counting-sort scatter of (point index, sign) into bucket order: position = bucket offset + rank.  Entry
-        //    arrays beyond L2 go through the two-pass partitioned scatter (msm_kernels.cuh)
-        if (n_entries * 4 > SCATTER_TWO_PASS_BYTES) k_scatter_partitioned(s, cnt, codes, ranks, pl, offsets, n_entries, part_cursor, staging, entries);
-        else k_scatter_ranked(s, cnt, codes, ranks, pl, offsets, entries);
-        if (k == 0) dv.timer.mark(3, s);
-        // 4. bucket accumulation (the hot kernel) + fold of split buckets
-        size_t split_buckets = n_entries / item_max + 1, split_items = 2 * split_buckets + 16;
-        k_accumulate<F>(s, total + split_items, pts, entries, items, bins + nbins, buckets, chunk_out, add_to);
-        k_chunk_merge<F>(s, split_buckets, split_list, chunk_out, buckets, add_to, dv.sm_count);
+        job.front(d_scalars + lo * 8, lo, cnt, mont, k == 0);
+        job.accumulate(k > 0);   // later ranges continue the bucket sums of the earlier ones
     }
-    dv.timer.mark(4, s);
-    // (prove schedule: stages 5-6 move to the lane's high-priority stream, see Device::tail_stream)
-    const stream_t main_stream = s;
-    if (split_tail) {
-        s = tail_stream_of(dv);
-        stream_wait(s, main_stream);
-    }
-    // 5. parallel bucket reduction: thread levels while the level is work bound (every thread walks 2^log_l
-    //    consecutive buckets), then block-cooperative levels (quad additions, scan + tree) for the latency
-    //    bound top of the tree
-    const uint32_t *X = buckets, *Y1 = nullptr, *Y2 = nullptr;
-    uint32_t n_in = plan.nb, shift = 0;
-    int flip = 0;
-    constexpr size_t PWORDS = 4 * FieldWords<F>::N;
-    size_t TILE_LEVEL_MAX, THREAD_LEVEL_GROUPS;
-    reduce_split((size_t)plan.bwin * plan.nb, TILE_LEVEL_MAX, THREAD_LEVEL_GROUPS);
-    while (n_in > 1) {
-        uint32_t n_out, log_l;
-        if ((size_t)plan.bwin * n_in > TILE_LEVEL_MAX) {
-            // aim at ~2^16 groups: fewer and the serial walk (2 x 2^log_l dependent additions) is latency
-            // bound, more and the tile levels above get more blocks than one wave
-            log_l = 2;
-            while (log_l < REDUCE_LOG_L && ((size_t)plan.bwin * n_in >> log_l) > THREAD_LEVEL_GROUPS) ++log_l;
-            uint32_t L = 1u << log_l;
-            n_out = (n_in + L - 1) / L;
-            uint32_t *Xo = ws.red[flip].as<uint32_t>((size_t)plan.bwin * n_out * PWORDS);
-            uint32_t *Yo = ws.red[flip + 1].as<uint32_t>((size_t)plan.bwin * n_out * PWORDS);
-            k_reduce_level<F>(s, (size_t)plan.bwin * n_out, X, Y1, n_in, n_out, L, shift, Xo, Yo);
-            X = Xo; Y1 = Yo;
-        } else {
-            uint32_t tile_max = k_tile_entries();
-            log_l = 1;
-            while ((1u << log_l) < n_in && (1u << log_l) < tile_max) ++log_l;
-            uint32_t T = 1u << log_l;
-            n_out = (n_in + T - 1) / T;
-            uint32_t *Xo = ws.red[flip].as<uint32_t>((size_t)plan.bwin * n_out * PWORDS);
-            uint32_t *Y1o = ws.red[flip + 1].as<uint32_t>((size_t)plan.bwin * n_out * PWORDS);
-            uint32_t *Y2o = (Y1 || Y2) ? ws.red[flip + 2].as<uint32_t>((size_t)plan.bwin * n_out * PWORDS) : nullptr;
-            k_tile_reduce<F>(s, plan.bwin, X, Y1, Y2, n_in, n_out, T, shift, Xo, Y1o, Y2o);
-            X = Xo; Y1 = Y1o; Y2 = Y2o;
-        }
-        n_in = n_out; shift += log_l; flip ^= 3;
-    }
-    dv.timer.mark(5, s);
-    // 6. window fold + to affine
-    k_window_combine<F>(s, X, Y1, Y2, plan.bwin, plan.c, d_out_xyzz, d_out_aff);
-    dv.timer.mark(6, s);
-    if (split_tail) stream_wait(main_stream, s);   // later work on the lane sees the result and may reuse the workspace
+    job.back(d_out_xyzz, d_out_aff);
 }
 
 // Import host points (ark layout + infinity bytes) into a device shard.

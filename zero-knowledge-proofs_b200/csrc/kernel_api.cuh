@@ -70,6 +70,9 @@ void k_window_combine(stream_t s, const uint32_t *X, const uint32_t *Y, const ui
                       uint32_t *out_xyzz, uint32_t *out_aff);
 template <class F>
 void k_partial_combine(stream_t s, const uint32_t *partials, uint32_t k, uint32_t *out_xyzz, uint32_t *out_aff);
+// out_xyzz[j] = scalars[j] * aff[j] for n points (affine records `stride` words apart: x, y, infinity word)
+template <class F>
+void k_scalar_mul_affine(stream_t s, size_t n, const uint32_t *scalars, const uint32_t *aff, uint32_t stride, uint32_t *out_xyzz);
 // table[w * n + i] = affine(2^(c w) * pts[i]) for w < nwin (w = 0 is a copy)
 template <class F>
 void k_precompute_bases(stream_t s, size_t n, const uint32_t *pts, uint32_t c, uint32_t nwin, uint32_t *table);

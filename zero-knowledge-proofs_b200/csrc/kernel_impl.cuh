@@ -66,6 +66,10 @@ void k_partial_combine(stream_t s, const uint32_t *partials, uint32_t k, uint32_
     launch<PartialCombine<F>>(1, s, partials, k, out_xyzz, out_aff);
 }
 template <class F>
+void k_scalar_mul_affine(stream_t s, size_t n, const uint32_t *scalars, const uint32_t *aff, uint32_t stride, uint32_t *out_xyzz) {
+    launch<ScalarMulAffine<F>>(n, s, scalars, aff, stride, out_xyzz);
+}
+template <class F>
 void k_precompute_bases(stream_t s, size_t n, const uint32_t *pts, uint32_t c, uint32_t nwin, uint32_t *table) {
     launch<PrecomputeBases<F>>(n, s, pts, n, c, nwin, table);
 }

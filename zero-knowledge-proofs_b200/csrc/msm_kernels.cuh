@@ -698,6 +698,31 @@ struct WindowCombine {
     }
 };
 
+// out[j] = scalar_j * P_j for a handful of points (prove: s * pi_A and r * pi_B', crates/groth16-core/src/lib.rs:235,259),
+// one thread per point, double-and-add from the top bit with mixed additions.  scalars: Montgomery Fr (8 words each);
+// aff: affine result records as WindowCombine / PartialCombine write them (x, y, infinity word), `stride` words apart.
+// ~255 doublings + ~128 mixed additions in a chain: 2 ms of latency, which the prove schedule hides under the bucket
+// accumulation of the MSMs that are still running.
+template <class F>
+struct ScalarMulAffine {
+    static constexpr int BLOCK = 32;
+    G16_HD static void run(size_t j, const uint32_t *scalars, const uint32_t *aff, uint32_t stride, uint32_t *out_xyzz) {
+        uint32_t k[8];
+        load_scalar(scalars, j, true, k);
+        const uint32_t *src = aff + j * stride;
+        Affine<F> p;
+        uint32_t *dx = limbs(p.x), *dy = limbs(p.y);
+        for (int w = 0; w < F::N; ++w) { dx[w] = src[w]; dy[w] = src[F::N + w]; }
+        XYZZ<F> acc = XYZZ<F>::inf();
+        if (!src[2 * F::N])
+            for (int bit = 254; bit >= 0; --bit) {
+                xyzz_dbl_call(acc);
+                if ((k[bit >> 5] >> (bit & 31)) & 1u) xyzz_madd_call(acc, p.x, p.y);
+            }
+        store_xyzz<F>(out_xyzz, j, acc);
+    }
+};
+
 // Sum of k projective partial results (multi-GPU combine), then to affine.
 template <class F>
 struct PartialCombine {

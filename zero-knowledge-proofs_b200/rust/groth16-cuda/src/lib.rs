@@ -67,6 +67,14 @@ impl Context {
         check(self.raw, unsafe { g16_ctx_last_stage_ms(self.raw, ms.as_mut_ptr(), plan.as_mut_ptr()) })?;
         Ok((ms, [plan[0] as u32, plan[1] as u32, plan[2] as u32]))
     }
+    /// With stage timing enabled: ms from the start of the last `prove` to the seven stage marks of its five lanes.
+    pub fn prove_timeline(&self) -> Result<[[f32; 7]; 5], String> {
+        let mut t = [0f32; 35];
+        check(self.raw, unsafe { g16_ctx_prove_timeline(self.raw, t.as_mut_ptr()) })?;
+        let mut out = [[0f32; 7]; 5];
+        for lane in 0..5 { out[lane].copy_from_slice(&t[7 * lane..7 * lane + 7]); }
+        Ok(out)
+    }
 }
 impl Drop for Context { fn drop(&mut self) { unsafe { g16_ctx_destroy(self.raw) } } }
 

@@ -110,6 +110,7 @@ extern "C" {
     pub fn g16_launch_count() -> c_ulonglong;
     pub fn g16_ctx_enable_stage_timing(ctx: *mut g16_ctx, on: c_int) -> c_int;
     pub fn g16_ctx_last_stage_ms(ctx: *mut g16_ctx, ms: *mut f32, plan: *mut c_uint) -> c_int;
+    pub fn g16_ctx_prove_timeline(ctx: *mut g16_ctx, t: *mut f32) -> c_int;
     pub fn g16_debug_fq_op(ctx: *mut g16_ctx, op: c_int, a: *const u64, b: *const u64, out: *mut u64, n: usize) -> c_int;
     pub fn g16_debug_fr_from_mont(ctx: *mut g16_ctx, a: *const u64, out: *mut u64, n: usize) -> c_int;
     pub fn g16_debug_g1_add(ctx: *mut g16_ctx, p: *const u64, p_inf: *const u8, q: *const u64, q_inf: *const u8, out_xy: *mut u64, out_inf: *mut u8, n: usize) -> c_int;

@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-precompute", action="store_true")
+    ap.add_argument("--timeline", action="store_true", help="print the per-lane stage timeline of one prove")
     ap.add_argument("--lib", default=None, help="alternative build of the library (A/B experiments, tools/lab_build.py)")
     args = ap.parse_args()
     import torch
@@ -81,6 +82,18 @@ def main():
         for _ in range(args.steps):
             proof = ctx.prove(dev_pk, w, h, r, s)
         gpu_ms = (time.perf_counter() - t0) / args.steps * 1e3
+        if args.timeline:   # one more prove with the per-lane stage marks
+            import ctypes
+            ctx.lib.g16_ctx_enable_stage_timing.argtypes = [ctypes.c_void_p, ctypes.c_int]
+            ctx.lib.g16_ctx_prove_timeline.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+            ctx.lib.g16_ctx_enable_stage_timing(ctx.handle, 1)
+            ctx.prove(dev_pk, w, h, r, s)
+            tl = (ctypes.c_float * 35)()
+            ctx._check(ctx.lib.g16_ctx_prove_timeline(ctx.handle, tl))
+            ctx.lib.g16_ctx_enable_stage_timing(ctx.handle, 0)
+            names = ["pi_A", "pi_B(G2)", "H", "pi_B'", "pi_C"]
+            for lane in range(5):
+                print("timeline", dist, names[lane], [round(float(tl[7 * lane + k]), 2) for k in range(7)], flush=True)
         line = {"metric": "groth16_prove_ms", "config": f"synthetic ProvingKey, N = n = 2^{args.log_n}, 1 public input, {dist}",
                 "gpu_ms": gpu_ms, "n_gpus": 1, "msms": "4 x G1 + 1 x G2 (+ ad-hoc terms)", "pk_generate_s": gen_s,
                 "pk_upload_s": upload_s}
