@@ -65,9 +65,13 @@ void g16_ctx_destroy(g16_ctx *ctx) {
 #endif
         d.ws.release();
         d.timer.destroy();
+#ifndef G16_EMU
+        if (d.tail_stream) { cudaStreamSynchronize(d.tail_stream); cudaStreamDestroy(d.tail_stream); }
+#endif
         for (auto &l : d.extra) {
 #ifndef G16_EMU
             if (l->stream) cudaStreamSynchronize(l->stream);
+            if (l->tail_stream) { cudaStreamSynchronize(l->tail_stream); cudaStreamDestroy(l->tail_stream); }
 #endif
             l->ws.release();
             l->timer.destroy();
@@ -481,28 +485,31 @@ void prove_single_device(Context *c, const g16_pk *pk, const uint64_t *w, size_t
         have = false;
     };
     auto passed = [&](Device &L) { done = event_record(L.stream); have = true; };
+    stream_t TA = tail_stream_of(LA), TB = tail_stream_of(LB), TH = tail_stream_of(LH), TB1 = tail_stream_of(LB1);
     gate(LA); ja.accumulate(false); passed(LA);
-    ja.back(nullptr, oa);
-    k_scalar_mul_affine<Fq>(LA.stream, 1, d_small + 6 * 8, oa, (uint32_t)AW1, t_sa);
+    ja.back(nullptr, oa, true);
+    k_scalar_mul_affine<Fq>(TA, 1, d_small + 6 * 8, oa, (uint32_t)AW1, t_sa);
     gate(LB1); jb1.accumulate(false); passed(LB1);
-    jb1.back(nullptr, ob1);
-    k_scalar_mul_affine<Fq>(LB1.stream, 1, d_small + 7 * 8, ob1, (uint32_t)AW1, t_rb1);
+    jb1.back(nullptr, ob1, true);
+    k_scalar_mul_affine<Fq>(TB1, 1, d_small + 7 * 8, ob1, (uint32_t)AW1, t_rb1);
     gate(LB); jb2.accumulate(false); passed(LB);
-    jb2.back(nullptr, ob);
-    if (jh) { gate(LH); jh->accumulate(false); passed(LH); jh->back(t_h, nullptr); }
-    else k_partial_combine<Fq>(LH.stream, nullptr, 0u, t_h, nullptr);
-    if (jc) { gate(LC); jc->accumulate(false); passed(LC); jc->back(t_priv, nullptr); }
+    jb2.back(nullptr, ob, true);
+    if (jh) { gate(LH); jh->accumulate(false); passed(LH); jh->back(t_h, nullptr, true); }
+    else k_partial_combine<Fq>(TH, nullptr, 0u, t_h, nullptr);
+    // the last accumulation has nothing to hide its tail under: big blocks on its own stream
+    if (jc) { gate(LC); jc->accumulate(false); passed(LC); jc->back(t_priv, nullptr, false); }
     else k_partial_combine<Fq>(LC.stream, nullptr, 0u, t_priv, nullptr);
     if (have) { event_wait_and_release(LC.stream, done); have = false; }
     // 4. pi_C on lane 4 once the other three terms exist (device-side dependency, no host wait)
-    for (Device *l : {&LA, &LH, &LB1}) stream_wait(LC.stream, l->stream);
+    for (stream_t t : {TA, TH, TB1}) stream_wait(LC.stream, t);
     k_partial_combine<Fq>(LC.stream, d_cparts, 4, nullptr, d_c_aff);
 
     uint32_t ra[AW1], rb[AW2], rc[AW1];
-    copy_d2h(ra, oa, AW1 * 4, LA.stream);
-    copy_d2h(rb, ob, AW2 * 4, LB.stream);
+    copy_d2h(ra, oa, AW1 * 4, TA);
+    copy_d2h(rb, ob, AW2 * 4, TB);
     copy_d2h(rc, d_c_aff, AW1 * 4, LC.stream);
     if (dev && dev->d_flags && dev->flags_out) copy_d2h(dev->flags_out, dev->d_flags, 8, LA.stream);
+    for (stream_t t : {TA, TB, TH, TB1}) stream_sync(t);
     for (Device *l : {&LA, &LB, &LH, &LB1, &LC}) stream_sync(l->stream);
     memcpy(a_xy, ra, 96); memcpy(b_xy, rb, 192); memcpy(c_xy, rc, 96);
     if (a_inf) *a_inf = (uint8_t)ra[24];
