@@ -65,13 +65,9 @@ void g16_ctx_destroy(g16_ctx *ctx) {
 #endif
         d.ws.release();
         d.timer.destroy();
-#ifndef G16_EMU
-        if (d.tail_stream) { cudaStreamSynchronize(d.tail_stream); cudaStreamDestroy(d.tail_stream); }
-#endif
         for (auto &l : d.extra) {
 #ifndef G16_EMU
             if (l->stream) cudaStreamSynchronize(l->stream);
-            if (l->tail_stream) { cudaStreamSynchronize(l->tail_stream); cudaStreamDestroy(l->tail_stream); }
 #endif
             l->ws.release();
             l->timer.destroy();
@@ -395,16 +391,18 @@ void g16_pk_free(g16_pk *pk) { delete pk; }
 
 extern "C++" {
 // Single-device fast path of the prove schedule.  The assignment is copied to the device once and every MSM gets its
-// (prefix ++ assignment) scalar vector by a device-to-device copy.  The five big MSMs live on five lanes (stream +
-// workspace each) and are ordered explicitly:
-//   1. the sort stages (digits, offsets, work items, counting sort) of ALL five run first -- they are short, and
-//      queued behind another lane's accumulation grid they would sit there for its whole duration;
-//   2. the bucket accumulations (the multiplier-bound part, each fills the GPU) run one after the other in the order
-//      pi_A, pi_B', pi_B (G2), H, private part of pi_C, chained by events;
-//   3. every lane's latency-bound tail (bucket reduction tree, fold, inversion) follows its accumulation on its own
-//      stream, i.e. under the accumulation of the next lanes; so do s * pi_A and r * pi_B' (2 ms double-and-add
-//      chains, ScalarMulAffine) -- which is why pi_A and pi_B' accumulate first;
-//   4. pi_C = private part + H + s pi_A + r pi_B' is one four-term fold on the device; the host waits once, at the end.
+// (prefix ++ assignment) scalar vector by a device-to-device copy.  The five big MSMs run on five lanes (stream +
+// workspace each), queued in the order pi_A, pi_B', pi_B (G2), H, private part of pi_C: the GPU works through the
+// bucket accumulations roughly in that order, so pi_A and pi_B' are known early and s * pi_A, r * pi_B' (2 ms
+// double-and-add chains, ScalarMulAffine) run on their lanes while the later accumulations keep the GPU busy.
+// pi_C = private part + H + s pi_A + r pi_B' is then one four-term fold on the device; the host waits once, at the end.
+//
+// Measured and not adopted (profiles/r02_run{9,10,11}_prove_timeline_*.txt): the whole prove is bound by the SUM of the
+// work of its kernels -- blocks of a younger grid are not dispatched while an older grid of the same priority has
+// pending blocks, so tails queue behind the accumulation grids of the other lanes; running them underneath instead
+// (high-priority streams, blocks small enough for the registers one retiring accumulate block frees, accumulations
+// chained by events) moved them but gained nothing at full width and lost 3.5 ms with the reference's 64-bit scalars:
+// the G2 bucket reduction is 5 ms of real multiplier work at low efficiency, wherever it runs.
 void prove_single_device(Context *c, const g16_pk *pk, const uint64_t *w, size_t num_vars, const uint64_t *h,
                          size_t num_h, const uint64_t *r, const uint64_t *s, uint64_t *a_xy, uint8_t *a_inf,
                          uint64_t *b_xy, uint8_t *b_inf, uint64_t *c_xy, uint8_t *c_inf, const ProveDeviceInputs *dev) {
@@ -471,45 +469,24 @@ void prove_single_device(Context *c, const g16_pk *pk, const uint64_t *w, size_t
     MsmJob<Fq2> jb2(LB, pk->b2->shards[0], nb2 + 2, co, 0);
     std::unique_ptr<MsmJob<Fq>> jh(nh ? new MsmJob<Fq>(LH, pk->h->shards[0], nh, co, 0) : nullptr);
     std::unique_ptr<MsmJob<Fq>> jc(nic ? new MsmJob<Fq>(LC, pk->ic->shards[0], nic, co, 0) : nullptr);
-    // 1. sort stages of all lanes
-    ja.front(sc_a, 0, na + 2, true, true);
-    jb1.front(sc_b1, 0, nb1 + 1, true, true);
-    jb2.front(sc_b2, 0, nb2 + 2, true, true);
-    if (jh) jh->front(sc_h, 0, nh, true, true);
-    if (jc) jc->front(d_w + first_priv * 8, 0, nic, true, true);
-    // 2. + 3. accumulations one after the other, every tail right behind its accumulation on its own stream
-    event_t done = nullptr;
-    bool have = false;
-    auto gate = [&](Device &L) {            // this lane's accumulation starts when the previous one has finished
-        if (have) event_wait_and_release(L.stream, done);
-        have = false;
-    };
-    auto passed = [&](Device &L) { done = event_record(L.stream); have = true; };
-    stream_t TA = tail_stream_of(LA), TB = tail_stream_of(LB), TH = tail_stream_of(LH), TB1 = tail_stream_of(LB1);
-    gate(LA); ja.accumulate(false); passed(LA);
-    ja.back(nullptr, oa, true);
-    k_scalar_mul_affine<Fq>(TA, 1, d_small + 6 * 8, oa, (uint32_t)AW1, t_sa);
-    gate(LB1); jb1.accumulate(false); passed(LB1);
-    jb1.back(nullptr, ob1, true);
-    k_scalar_mul_affine<Fq>(TB1, 1, d_small + 7 * 8, ob1, (uint32_t)AW1, t_rb1);
-    gate(LB); jb2.accumulate(false); passed(LB);
-    jb2.back(nullptr, ob, true);
-    if (jh) { gate(LH); jh->accumulate(false); passed(LH); jh->back(t_h, nullptr, true); }
-    else k_partial_combine<Fq>(TH, nullptr, 0u, t_h, nullptr);
-    // the last accumulation has nothing to hide its tail under: big blocks on its own stream
-    if (jc) { gate(LC); jc->accumulate(false); passed(LC); jc->back(t_priv, nullptr, false); }
+    ja.front(sc_a, 0, na + 2, true, true); ja.accumulate(false); ja.back(nullptr, oa);
+    k_scalar_mul_affine<Fq>(LA.stream, 1, d_small + 6 * 8, oa, (uint32_t)AW1, t_sa);
+    jb1.front(sc_b1, 0, nb1 + 1, true, true); jb1.accumulate(false); jb1.back(nullptr, ob1);
+    k_scalar_mul_affine<Fq>(LB1.stream, 1, d_small + 7 * 8, ob1, (uint32_t)AW1, t_rb1);
+    jb2.front(sc_b2, 0, nb2 + 2, true, true); jb2.accumulate(false); jb2.back(nullptr, ob);
+    if (jh) { jh->front(sc_h, 0, nh, true, true); jh->accumulate(false); jh->back(t_h, nullptr); }
+    else k_partial_combine<Fq>(LH.stream, nullptr, 0u, t_h, nullptr);
+    if (jc) { jc->front(d_w + first_priv * 8, 0, nic, true, true); jc->accumulate(false); jc->back(t_priv, nullptr); }
     else k_partial_combine<Fq>(LC.stream, nullptr, 0u, t_priv, nullptr);
-    if (have) { event_wait_and_release(LC.stream, done); have = false; }
-    // 4. pi_C on lane 4 once the other three terms exist (device-side dependency, no host wait)
-    for (stream_t t : {TA, TH, TB1}) stream_wait(LC.stream, t);
+    // pi_C on lane 4 once the other three terms exist (device-side dependency, no host wait)
+    for (Device *l : {&LA, &LH, &LB1}) stream_wait(LC.stream, l->stream);
     k_partial_combine<Fq>(LC.stream, d_cparts, 4, nullptr, d_c_aff);
 
     uint32_t ra[AW1], rb[AW2], rc[AW1];
-    copy_d2h(ra, oa, AW1 * 4, TA);
-    copy_d2h(rb, ob, AW2 * 4, TB);
+    copy_d2h(ra, oa, AW1 * 4, LA.stream);
+    copy_d2h(rb, ob, AW2 * 4, LB.stream);
     copy_d2h(rc, d_c_aff, AW1 * 4, LC.stream);
     if (dev && dev->d_flags && dev->flags_out) copy_d2h(dev->flags_out, dev->d_flags, 8, LA.stream);
-    for (stream_t t : {TA, TB, TH, TB1}) stream_sync(t);
     for (Device *l : {&LA, &LB, &LH, &LB1, &LC}) stream_sync(l->stream);
     memcpy(a_xy, ra, 96); memcpy(b_xy, rb, 192); memcpy(c_xy, rc, 96);
     if (a_inf) *a_inf = (uint8_t)ra[24];

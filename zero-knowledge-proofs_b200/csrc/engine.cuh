@@ -89,12 +89,6 @@ struct Device {
     // extra lanes (own stream + workspace) on the same GPU: lets the latency-bound tail of one MSM
     // (reduction tree, inversion) overlap the bucket accumulation of another (prove schedule)
     std::vector<std::unique_ptr<Device>> extra;
-    // High-priority stream for the latency-bound tail of an MSM (bucket reduction tree, fold, inversion) when several
-    // MSMs share the GPU (prove schedule).  Blocks of a younger grid are not dispatched while an older grid of the same
-    // priority still has pending blocks, so a tail queued behind another lane's accumulation grid would wait for all of
-    // it (measured: profiles/r02_run10_prove_timeline_chained_accumulations.txt); with priority, and with blocks small
-    // enough for the registers one retiring accumulate block frees, it runs underneath.  Created on first use.
-    stream_t tail_stream = nullptr;
 };
 
 inline void set_device(int id);
@@ -128,19 +122,6 @@ inline void set_device(int id) {
     (void)id;
 #endif
 }
-inline stream_t tail_stream_of(Device &dv) {
-#ifndef G16_EMU
-    if (!dv.tail_stream) {
-        int least = 0, greatest = 0;
-        G16_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
-        G16_CUDA_CHECK(cudaStreamCreateWithPriority(&dv.tail_stream, cudaStreamNonBlocking, greatest));
-    }
-    return dv.tail_stream;
-#else
-    return dv.stream;
-#endif
-}
-
 // Host-scalar MSMs of at least `h2d_pipe_min` scalars are cut into H2D_PIPE_PARTS index ranges of growing size
 // (1/32, 5/32, 26/32 of the scalars).  The ranges are copied back to back on a second stream; each one is decomposed,
 // sorted and accumulated INTO THE SAME bucket array as soon as it has arrived, and the buckets are reduced once at the
@@ -364,17 +345,11 @@ struct MsmJob {
         k_chunk_merge<F>(s, split_buckets, split_list, chunk_out, buckets, add_to, dv.sm_count);
     }
 
-    // stages 5-6.  d_out_xyzz: 4 * FieldWords<F>::N words (may be null), d_out_aff: 2 * FieldWords<F>::N + 1 words (may be null).
-    // under_other_work: the tail runs on the lane's high-priority stream with small blocks, next to the accumulation of
-    // other lanes (the caller orders later work on the lane after tail_stream_of(dv)); otherwise on dv.stream
-    void back(uint32_t *d_out_xyzz, uint32_t *d_out_aff, bool under_other_work = false) {
+    // stages 5-6.  d_out_xyzz: 4 * FieldWords<F>::N words (may be null), d_out_aff: 2 * FieldWords<F>::N + 1 words (may be null)
+    void back(uint32_t *d_out_xyzz, uint32_t *d_out_aff) {
         stream_t s = dv.stream;
         Workspace &ws = dv.ws;
         dv.timer.mark(4, s);
-        if (under_other_work) {
-            s = tail_stream_of(dv);
-            stream_wait(s, dv.stream);
-        }
         // 5. parallel bucket reduction: thread levels while the level is work bound (every thread walks 2^log_l
         //    consecutive buckets), then block-cooperative levels (quad additions, scan + tree) for the latency
         //    bound top of the tree
@@ -398,7 +373,7 @@ struct MsmJob {
                 k_reduce_level<F>(s, (size_t)plan.bwin * n_out, X, Y1, n_in, n_out, L, shift, Xo, Yo);
                 X = Xo; Y1 = Yo;
             } else {
-                uint32_t tile_max = k_tile_entries(under_other_work);
+                uint32_t tile_max = k_tile_entries();
                 log_l = 1;
                 while ((1u << log_l) < n_in && (1u << log_l) < tile_max) ++log_l;
                 uint32_t T = 1u << log_l;
@@ -406,7 +381,7 @@ struct MsmJob {
                 uint32_t *Xo = ws.red[flip].as<uint32_t>((size_t)plan.bwin * n_out * PWORDS);
                 uint32_t *Y1o = ws.red[flip + 1].as<uint32_t>((size_t)plan.bwin * n_out * PWORDS);
                 uint32_t *Y2o = (Y1 || Y2) ? ws.red[flip + 2].as<uint32_t>((size_t)plan.bwin * n_out * PWORDS) : nullptr;
-                k_tile_reduce<F>(s, plan.bwin, X, Y1, Y2, n_in, n_out, T, shift, Xo, Y1o, Y2o, under_other_work);
+                k_tile_reduce<F>(s, plan.bwin, X, Y1, Y2, n_in, n_out, T, shift, Xo, Y1o, Y2o);
                 X = Xo; Y1 = Y1o; Y2 = Y2o;
             }
             n_in = n_out; shift += log_l; flip ^= 3;

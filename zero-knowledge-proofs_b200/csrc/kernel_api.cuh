@@ -60,13 +60,11 @@ void k_chunk_merge(stream_t s, size_t max_split, const uint32_t *split_list, con
 template <class F>
 void k_reduce_level(stream_t s, size_t threads, const uint32_t *X, const uint32_t *Y, uint32_t n_in, uint32_t n_out,
                     uint32_t L, uint32_t shift, uint32_t *Xo, uint32_t *Yo);
-// block-cooperative level: tile = T entries (power of two <= k_tile_entries(small)), grid (n_out, windows, X | Y blocks).
-// small: 64-thread blocks (16 elements) instead of 256 -- a block then fits the registers one retiring accumulate block
-// frees, so the level can run next to another lane's bucket accumulation (prove schedule); two more doublings of latency
-uint32_t k_tile_entries(bool small = false);
+// block-cooperative level: tile = T entries (power of two <= k_tile_entries()), grid (n_out, windows, X | Y blocks)
+uint32_t k_tile_entries();
 template <class F>
 void k_tile_reduce(stream_t s, uint32_t windows, const uint32_t *X, const uint32_t *Y1, const uint32_t *Y2, uint32_t n_in,
-                   uint32_t n_out, uint32_t T, uint32_t shift, uint32_t *Xo, uint32_t *Y1o, uint32_t *Y2o, bool small = false);
+                   uint32_t n_out, uint32_t T, uint32_t shift, uint32_t *Xo, uint32_t *Y1o, uint32_t *Y2o);
 template <class F>
 void k_window_combine(stream_t s, const uint32_t *X, const uint32_t *Y, const uint32_t *Y2, uint32_t nwin, uint32_t c,
                       uint32_t *out_xyzz, uint32_t *out_aff);

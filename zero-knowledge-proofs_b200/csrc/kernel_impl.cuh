@@ -35,8 +35,7 @@ void k_reduce_level(stream_t s, size_t threads, const uint32_t *X, const uint32_
 }
 template <class F>
 void k_tile_reduce(stream_t s, uint32_t windows, const uint32_t *X, const uint32_t *Y1, const uint32_t *Y2, uint32_t n_in,
-                   uint32_t n_out, uint32_t T, uint32_t shift, uint32_t *Xo, uint32_t *Y1o, uint32_t *Y2o, bool small) {
-    (void)small;   // the tile size T already reflects it (k_tile_entries(small)); the block is 4 lanes per T / TILE_K elements
+                   uint32_t n_out, uint32_t T, uint32_t shift, uint32_t *Xo, uint32_t *Y1o, uint32_t *Y2o) {
 #ifndef G16_EMU
     // T = entries per tile; elements (quads of lanes) = T / TILE_K, at least one warp of 8
     uint32_t elems = T / TILE_K < 8 ? 8 : T / TILE_K;
