@@ -65,9 +65,13 @@ void g16_ctx_destroy(g16_ctx *ctx) {
 #endif
         d.ws.release();
         d.timer.destroy();
+#ifndef G16_EMU
+        if (d.tail_stream) { cudaStreamSynchronize(d.tail_stream); cudaStreamDestroy(d.tail_stream); }
+#endif
         for (auto &l : d.extra) {
 #ifndef G16_EMU
             if (l->stream) cudaStreamSynchronize(l->stream);
+            if (l->tail_stream) { cudaStreamSynchronize(l->tail_stream); cudaStreamDestroy(l->tail_stream); }
 #endif
             l->ws.release();
             l->timer.destroy();
@@ -469,24 +473,28 @@ void prove_single_device(Context *c, const g16_pk *pk, const uint64_t *w, size_t
     MsmJob<Fq2> jb2(LB, pk->b2->shards[0], nb2 + 2, co, 0);
     std::unique_ptr<MsmJob<Fq>> jh(nh ? new MsmJob<Fq>(LH, pk->h->shards[0], nh, co, 0) : nullptr);
     std::unique_ptr<MsmJob<Fq>> jc(nic ? new MsmJob<Fq>(LC, pk->ic->shards[0], nic, co, 0) : nullptr);
-    ja.front(sc_a, 0, na + 2, true, true); ja.accumulate(false); ja.back(nullptr, oa);
-    k_scalar_mul_affine<Fq>(LA.stream, 1, d_small + 6 * 8, oa, (uint32_t)AW1, t_sa);
-    jb1.front(sc_b1, 0, nb1 + 1, true, true); jb1.accumulate(false); jb1.back(nullptr, ob1);
-    k_scalar_mul_affine<Fq>(LB1.stream, 1, d_small + 7 * 8, ob1, (uint32_t)AW1, t_rb1);
+    // pi_A and pi_B' first, their (cheap) tails urgent, so that the two multiplication chains run under the rest
+    ja.front(sc_a, 0, na + 2, true, true); ja.accumulate(false);
+    stream_t TA = ja.back(nullptr, oa, true);
+    k_scalar_mul_affine<Fq>(TA, 1, d_small + 6 * 8, oa, (uint32_t)AW1, t_sa);
+    jb1.front(sc_b1, 0, nb1 + 1, true, true); jb1.accumulate(false);
+    stream_t TB1 = jb1.back(nullptr, ob1, true);
+    k_scalar_mul_affine<Fq>(TB1, 1, d_small + 7 * 8, ob1, (uint32_t)AW1, t_rb1);
     jb2.front(sc_b2, 0, nb2 + 2, true, true); jb2.accumulate(false); jb2.back(nullptr, ob);
     if (jh) { jh->front(sc_h, 0, nh, true, true); jh->accumulate(false); jh->back(t_h, nullptr); }
     else k_partial_combine<Fq>(LH.stream, nullptr, 0u, t_h, nullptr);
     if (jc) { jc->front(d_w + first_priv * 8, 0, nic, true, true); jc->accumulate(false); jc->back(t_priv, nullptr); }
     else k_partial_combine<Fq>(LC.stream, nullptr, 0u, t_priv, nullptr);
     // pi_C on lane 4 once the other three terms exist (device-side dependency, no host wait)
-    for (Device *l : {&LA, &LH, &LB1}) stream_wait(LC.stream, l->stream);
+    for (stream_t t : {TA, LH.stream, TB1}) stream_wait(LC.stream, t);
     k_partial_combine<Fq>(LC.stream, d_cparts, 4, nullptr, d_c_aff);
 
     uint32_t ra[AW1], rb[AW2], rc[AW1];
-    copy_d2h(ra, oa, AW1 * 4, LA.stream);
+    copy_d2h(ra, oa, AW1 * 4, TA);
     copy_d2h(rb, ob, AW2 * 4, LB.stream);
     copy_d2h(rc, d_c_aff, AW1 * 4, LC.stream);
     if (dev && dev->d_flags && dev->flags_out) copy_d2h(dev->flags_out, dev->d_flags, 8, LA.stream);
+    stream_sync(TA); stream_sync(TB1);
     for (Device *l : {&LA, &LB, &LH, &LB1, &LC}) stream_sync(l->stream);
     memcpy(a_xy, ra, 96); memcpy(b_xy, rb, 192); memcpy(c_xy, rc, 96);
     if (a_inf) *a_inf = (uint8_t)ra[24];
