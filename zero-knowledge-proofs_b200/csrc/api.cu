@@ -65,13 +65,9 @@ void g16_ctx_destroy(g16_ctx *ctx) {
 #endif
         d.ws.release();
         d.timer.destroy();
-#ifndef G16_EMU
-        if (d.tail_stream) { cudaStreamSynchronize(d.tail_stream); cudaStreamDestroy(d.tail_stream); }
-#endif
         for (auto &l : d.extra) {
 #ifndef G16_EMU
             if (l->stream) cudaStreamSynchronize(l->stream);
-            if (l->tail_stream) { cudaStreamSynchronize(l->tail_stream); cudaStreamDestroy(l->tail_stream); }
 #endif
             l->ws.release();
             l->timer.destroy();
@@ -394,19 +390,20 @@ void g16_pk_free(g16_pk *pk) { delete pk; }
 
 
 extern "C++" {
-// Single-device fast path of the prove schedule.  The assignment is copied to the device once and every MSM gets its
-// (prefix ++ assignment) scalar vector by a device-to-device copy.  The five big MSMs run on five lanes (stream +
-// workspace each), queued in the order pi_A, pi_B', pi_B (G2), H, private part of pi_C: the GPU works through the
-// bucket accumulations roughly in that order, so pi_A and pi_B' are known early and s * pi_A, r * pi_B' (2 ms
-// double-and-add chains, ScalarMulAffine) run on their lanes while the later accumulations keep the GPU busy.
-// pi_C = private part + H + s pi_A + r pi_B' is then one four-term fold on the device; the host waits once, at the end.
+// Single-device fast path of the prove schedule: the assignment is copied to the device once, every MSM gets its
+// (prefix ++ assignment) scalar vector by a device-to-device copy, the five big MSMs run on five lanes (stream +
+// workspace each), and pi_C = private part + H + s pi_A + r pi_B' is finished on the device: the two multiplications
+// are double-and-add chains side by side in one warp (ScalarMulAffine, 2 ms; the 3-point MSM through the whole
+// pipeline that did this before cost 4 ms of serial window folding), then one four-term fold.  The host waits once.
 //
-// Measured and not adopted (profiles/r02_run{9,10,11}_prove_timeline_*.txt): the whole prove is bound by the SUM of the
-// work of its kernels -- blocks of a younger grid are not dispatched while an older grid of the same priority has
-// pending blocks, so tails queue behind the accumulation grids of the other lanes; running them underneath instead
-// (high-priority streams, blocks small enough for the registers one retiring accumulate block frees, accumulations
-// chained by events) moved them but gained nothing at full width and lost 3.5 ms with the reference's 64-bit scalars:
-// the G2 bucket reduction is 5 ms of real multiplier work at low efficiency, wherever it runs.
+// The prove is bound by the SUM of the work of its kernels, not by their latencies (profiles/r02_run{9..13}_prove_timeline_*.txt):
+// blocks of a younger grid are not dispatched while an older grid of the same priority has pending blocks, so sort stages
+// and tails of one lane queue behind the accumulation grids of the others, but the GPU is busy throughout.  Measured
+// against this schedule and not adopted: sort stages of all lanes first + accumulations chained by events + tails on
+// high-priority streams with blocks small enough for the registers one retiring accumulate block frees (same 52.5 ms at
+// full width, 30.8 instead of 27.3 ms with the reference's 64-bit scalars: the G2 bucket reduction is 5 ms of real
+// multiplier work at low efficiency wherever it runs, and small tail blocks cost an extra tree level); the same for
+// pi_A and pi_B' only (54.3 / 30.4 ms); independent lanes with the chains on the producing lanes (56.9 / 30.9 ms).
 void prove_single_device(Context *c, const g16_pk *pk, const uint64_t *w, size_t num_vars, const uint64_t *h,
                          size_t num_h, const uint64_t *r, const uint64_t *s, uint64_t *a_xy, uint8_t *a_inf,
                          uint64_t *b_xy, uint8_t *b_inf, uint64_t *c_xy, uint8_t *c_inf, const ProveDeviceInputs *dev) {
@@ -422,7 +419,7 @@ void prove_single_device(Context *c, const g16_pk *pk, const uint64_t *w, size_t
         G16_CUDA_CHECK(cudaEventRecord((cudaEvent_t)c->prove_epoch, LA.stream));
     }
 #endif
-    // small host staging block (kept alive until the final synchronisation): prefixes and ad-hoc scalars
+    // small host staging block (kept alive until the final synchronisation): prefixes and the two multipliers
     std::vector<uint64_t> hs(4 * 16);
     auto put = [&](size_t slot, const uint64_t *x) { memcpy(hs.data() + 4 * slot, x, 32); };
     put(0, FR_ONE_MONT); put(1, r);          // pi_A prefix   [1, r]
@@ -438,9 +435,10 @@ void prove_single_device(Context *c, const g16_pk *pk, const uint64_t *w, size_t
         copy_h2d(buf, w, num_vars * 32, LA.stream);
         d_w = buf;
     }
-    uint32_t *d_misc = LA.ws.prove_misc.as<uint32_t>(16 * 8 + 4 * PW1 + AW1 + 64);
+    uint32_t *d_misc = LA.ws.prove_misc.as<uint32_t>(16 * 8 + 2 * AW1 + 4 * PW1 + AW1 + 64);
     uint32_t *d_small = d_misc;                       // 16 scalars
-    uint32_t *d_cparts = d_misc + 16 * 8;             // 4 projective terms of pi_C: private part, H, s pi_A, r pi_B'
+    uint32_t *d_ab1 = d_misc + 16 * 8;                // pi_A and pi_B' affine records, back to back (inputs of the chains)
+    uint32_t *d_cparts = d_ab1 + 2 * AW1;             // 4 projective terms of pi_C: private part, H, s pi_A, r pi_B'
     uint32_t *d_c_aff = d_cparts + 4 * PW1;           // pi_C affine
     copy_h2d(d_small, hs.data(), 16 * 32, LA.stream);
     for (Device *l : {&LB, &LB1, &LC}) stream_wait(l->stream, LA.stream);
@@ -450,51 +448,40 @@ void prove_single_device(Context *c, const g16_pk *pk, const uint64_t *w, size_t
         uint32_t *d = L.ws.scalars.as<uint32_t>((k + n) * 8 + 8);
         copy_d2d(d, d_small + slot * 8, k * 32, L.stream);
         copy_d2d(d + k * 8, d_w, n * 32, L.stream);
-        return (const uint32_t *)d;
+        return d;
     };
+    // pi_A (lane 0), pi_B in G2 (lane 1), [H(s)]_1 (lane 2), pi_B' (lane 3), private part of pi_C (lane 4)
     size_t na = std::min(num_vars, pk->a_len), nb2 = std::min(num_vars, pk->b2_len), nb1 = std::min(num_vars, pk->b1_len);
+    uint32_t *t_priv = d_cparts, *t_h = d_cparts + PW1, *t_mul = d_cparts + 2 * PW1;
+    uint32_t *oa = LA.ws.out.as<uint32_t>(PW1 + AW1) + PW1;
+    msm_run<Fq>(LA, pk->a->shards[0], prefixed(LA, 0, 2, na), na + 2, true, co, nullptr, oa);
+    uint32_t *ob = LB.ws.out.as<uint32_t>(PW2 + AW2) + PW2;
+    msm_run<Fq2>(LB, pk->b2->shards[0], prefixed(LB, 2, 2, nb2), nb2 + 2, true, co, nullptr, ob);
     size_t nh = (h || (dev && dev->d_h)) ? std::min(num_h, pk->h_len) : 0;
-    size_t first_priv = pk->num_public + 1;
-    size_t nic = num_vars > first_priv ? std::min(num_vars - first_priv, pk->ic_len) : 0;
-    const uint32_t *sc_a = prefixed(LA, 0, 2, na), *sc_b2 = prefixed(LB, 2, 2, nb2), *sc_b1 = prefixed(LB1, 4, 1, nb1);
-    const uint32_t *sc_h = dev ? dev->d_h : nullptr;
-    if (nh && !sc_h) {
+    if (dev && dev->d_h) {
+        msm_run<Fq>(LH, pk->h->shards[0], dev->d_h, nh, true, co, t_h, nullptr);
+    } else {
         uint32_t *d_h = LH.ws.scalars.as<uint32_t>(nh * 8 + 8);
         copy_h2d(d_h, h, nh * 32, LH.stream);
-        sc_h = d_h;
+        msm_run<Fq>(LH, pk->h->shards[0], d_h, nh, true, co, t_h, nullptr);     // nh == 0 -> identity
     }
-    uint32_t *oa = LA.ws.out.as<uint32_t>(PW1 + AW1) + PW1;      // pi_A affine
-    uint32_t *ob = LB.ws.out.as<uint32_t>(PW2 + AW2) + PW2;      // pi_B affine (G2)
-    uint32_t *ob1 = LB1.ws.out.as<uint32_t>(PW1 + AW1) + PW1;    // pi_B' affine
-    uint32_t *t_priv = d_cparts, *t_h = d_cparts + PW1, *t_sa = d_cparts + 2 * PW1, *t_rb1 = d_cparts + 3 * PW1;
-
-    // the five MSMs in accumulation order; an empty one (no H coefficients, no private variables) contributes the identity
-    MsmJob<Fq> ja(LA, pk->a->shards[0], na + 2, co, 0), jb1(LB1, pk->b1->shards[0], nb1 + 1, co, 0);
-    MsmJob<Fq2> jb2(LB, pk->b2->shards[0], nb2 + 2, co, 0);
-    std::unique_ptr<MsmJob<Fq>> jh(nh ? new MsmJob<Fq>(LH, pk->h->shards[0], nh, co, 0) : nullptr);
-    std::unique_ptr<MsmJob<Fq>> jc(nic ? new MsmJob<Fq>(LC, pk->ic->shards[0], nic, co, 0) : nullptr);
-    // pi_A and pi_B' first, their (cheap) tails urgent, so that the two multiplication chains run under the rest
-    ja.front(sc_a, 0, na + 2, true, true); ja.accumulate(false);
-    stream_t TA = ja.back(nullptr, oa, true);
-    k_scalar_mul_affine<Fq>(TA, 1, d_small + 6 * 8, oa, (uint32_t)AW1, t_sa);
-    jb1.front(sc_b1, 0, nb1 + 1, true, true); jb1.accumulate(false);
-    stream_t TB1 = jb1.back(nullptr, ob1, true);
-    k_scalar_mul_affine<Fq>(TB1, 1, d_small + 7 * 8, ob1, (uint32_t)AW1, t_rb1);
-    jb2.front(sc_b2, 0, nb2 + 2, true, true); jb2.accumulate(false); jb2.back(nullptr, ob);
-    if (jh) { jh->front(sc_h, 0, nh, true, true); jh->accumulate(false); jh->back(t_h, nullptr); }
-    else k_partial_combine<Fq>(LH.stream, nullptr, 0u, t_h, nullptr);
-    if (jc) { jc->front(d_w + first_priv * 8, 0, nic, true, true); jc->accumulate(false); jc->back(t_priv, nullptr); }
-    else k_partial_combine<Fq>(LC.stream, nullptr, 0u, t_priv, nullptr);
-    // pi_C on lane 4 once the other three terms exist (device-side dependency, no host wait)
-    for (stream_t t : {TA, LH.stream, TB1}) stream_wait(LC.stream, t);
+    uint32_t *ob1 = LB1.ws.out.as<uint32_t>(PW1 + AW1) + PW1;
+    msm_run<Fq>(LB1, pk->b1->shards[0], prefixed(LB1, 4, 1, nb1), nb1 + 1, true, co, nullptr, ob1);
+    size_t first_priv = pk->num_public + 1;
+    size_t nic = num_vars > first_priv ? std::min(num_vars - first_priv, pk->ic_len) : 0;
+    msm_run<Fq>(LC, pk->ic->shards[0], d_w + first_priv * 8, nic, true, co, t_priv, nullptr);
+    // the rest of pi_C on lane 4 once pi_A, H and pi_B' exist (device-side dependency, no host wait)
+    for (Device *l : {&LA, &LH, &LB1}) stream_wait(LC.stream, l->stream);
+    copy_d2d(d_ab1, oa, AW1 * 4, LC.stream);
+    copy_d2d(d_ab1 + AW1, ob1, AW1 * 4, LC.stream);
+    k_scalar_mul_affine<Fq>(LC.stream, 2, d_small + 6 * 8, d_ab1, (uint32_t)AW1, t_mul);
     k_partial_combine<Fq>(LC.stream, d_cparts, 4, nullptr, d_c_aff);
 
     uint32_t ra[AW1], rb[AW2], rc[AW1];
-    copy_d2h(ra, oa, AW1 * 4, TA);
+    copy_d2h(ra, oa, AW1 * 4, LA.stream);
     copy_d2h(rb, ob, AW2 * 4, LB.stream);
     copy_d2h(rc, d_c_aff, AW1 * 4, LC.stream);
     if (dev && dev->d_flags && dev->flags_out) copy_d2h(dev->flags_out, dev->d_flags, 8, LA.stream);
-    stream_sync(TA); stream_sync(TB1);
     for (Device *l : {&LA, &LB, &LH, &LB1, &LC}) stream_sync(l->stream);
     memcpy(a_xy, ra, 96); memcpy(b_xy, rb, 192); memcpy(c_xy, rc, 96);
     if (a_inf) *a_inf = (uint8_t)ra[24];

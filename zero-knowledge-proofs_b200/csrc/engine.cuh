@@ -89,11 +89,6 @@ struct Device {
     // extra lanes (own stream + workspace) on the same GPU: lets the latency-bound tail of one MSM
     // (reduction tree, inversion) overlap the bucket accumulation of another (prove schedule)
     std::vector<std::unique_ptr<Device>> extra;
-    // High-priority stream for the tail (bucket reduction tree, fold, inversion) of an MSM whose result other work is
-    // waiting for while the GPU is full of another lane's accumulation (prove schedule, pi_A and pi_B').  Blocks of a
-    // younger grid are not dispatched while an older grid of the same priority has pending blocks, so such a tail would
-    // otherwise sit behind ALL queued accumulations (profiles/r02_run12_prove_timeline_*.txt).  Created on first use.
-    stream_t tail_stream = nullptr;
 };
 
 inline void set_device(int id);
@@ -127,19 +122,6 @@ inline void set_device(int id) {
     (void)id;
 #endif
 }
-inline stream_t tail_stream_of(Device &dv) {
-#ifndef G16_EMU
-    if (!dv.tail_stream) {
-        int least = 0, greatest = 0;
-        G16_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
-        G16_CUDA_CHECK(cudaStreamCreateWithPriority(&dv.tail_stream, cudaStreamNonBlocking, greatest));
-    }
-    return dv.tail_stream;
-#else
-    return dv.stream;
-#endif
-}
-
 // Host-scalar MSMs of at least `h2d_pipe_min` scalars are cut into H2D_PIPE_PARTS index ranges of growing size
 // (1/32, 5/32, 26/32 of the scalars).  The ranges are copied back to back on a second stream; each one is decomposed,
 // sorted and accumulated INTO THE SAME bucket array as soon as it has arrived, and the buckets are reduced once at the
@@ -363,17 +345,11 @@ struct MsmJob {
         k_chunk_merge<F>(s, split_buckets, split_list, chunk_out, buckets, add_to, dv.sm_count);
     }
 
-    // stages 5-6.  d_out_xyzz: 4 * FieldWords<F>::N words (may be null), d_out_aff: 2 * FieldWords<F>::N + 1 words (may be null).
-    // urgent: run on the lane's high-priority stream (returned) with hole-sized blocks, see Device::tail_stream; the caller
-    // queues whatever consumes the result on that stream
-    stream_t back(uint32_t *d_out_xyzz, uint32_t *d_out_aff, bool urgent = false) {
+    // stages 5-6.  d_out_xyzz: 4 * FieldWords<F>::N words (may be null), d_out_aff: 2 * FieldWords<F>::N + 1 words (may be null)
+    void back(uint32_t *d_out_xyzz, uint32_t *d_out_aff) {
         stream_t s = dv.stream;
         Workspace &ws = dv.ws;
         dv.timer.mark(4, s);
-        if (urgent) {
-            s = tail_stream_of(dv);
-            stream_wait(s, dv.stream);
-        }
         // 5. parallel bucket reduction: thread levels while the level is work bound (every thread walks 2^log_l
         //    consecutive buckets), then block-cooperative levels (quad additions, scan + tree) for the latency
         //    bound top of the tree
@@ -394,10 +370,10 @@ struct MsmJob {
                 n_out = (n_in + L - 1) / L;
                 uint32_t *Xo = ws.red[flip].as<uint32_t>((size_t)plan.bwin * n_out * PWORDS);
                 uint32_t *Yo = ws.red[flip + 1].as<uint32_t>((size_t)plan.bwin * n_out * PWORDS);
-                k_reduce_level<F>(s, (size_t)plan.bwin * n_out, X, Y1, n_in, n_out, L, shift, Xo, Yo, urgent);
+                k_reduce_level<F>(s, (size_t)plan.bwin * n_out, X, Y1, n_in, n_out, L, shift, Xo, Yo);
                 X = Xo; Y1 = Yo;
             } else {
-                uint32_t tile_max = k_tile_entries(urgent);
+                uint32_t tile_max = k_tile_entries();
                 log_l = 1;
                 while ((1u << log_l) < n_in && (1u << log_l) < tile_max) ++log_l;
                 uint32_t T = 1u << log_l;
@@ -414,7 +390,6 @@ struct MsmJob {
         // 6. window fold + to affine
         k_window_combine<F>(s, X, Y1, Y2, plan.bwin, plan.c, d_out_xyzz, d_out_aff);
         dv.timer.mark(6, s);
-        return s;
     }
 };
 

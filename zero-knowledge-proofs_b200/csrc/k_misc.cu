@@ -46,7 +46,7 @@ void k_scatter_partitioned(stream_t s, size_t n, const uint32_t *codes, const ui
 size_t k_item_bins() { return ITEM_BINS; }
 size_t k_item_bytes() { return sizeof(WorkItem); }
 uint32_t k_item_max() { return ITEM_MAX; }
-uint32_t k_tile_entries(bool small) { return (uint32_t)(TILE_K * (small ? TILE_ELEMS_SMALL : TILE_ELEMS)); }
+uint32_t k_tile_entries() { return (uint32_t)(TILE_K * TILE_ELEMS); }
 void k_item_count(stream_t s, size_t buckets, const uint32_t *offsets, uint32_t item_max, uint32_t *bin_counts) {
 #ifndef G16_EMU
     if (!buckets) return;

@@ -59,12 +59,9 @@ void k_chunk_merge(stream_t s, size_t max_split, const uint32_t *split_list, con
                    bool add_to, uint32_t sm_count);
 template <class F>
 void k_reduce_level(stream_t s, size_t threads, const uint32_t *X, const uint32_t *Y, uint32_t n_in, uint32_t n_out,
-                    uint32_t L, uint32_t shift, uint32_t *Xo, uint32_t *Yo, bool small = false);
-// block-cooperative level: tile = T entries (power of two <= k_tile_entries(small)), grid (n_out, windows, X | Y blocks).
-// small: tiles of 64 entries = 64-thread blocks, and 32-thread blocks for the thread levels: such a block fits the
-// registers ONE retiring accumulate block frees, so the tail of a small MSM can run next to another lane's bucket
-// accumulation instead of behind it (prove schedule: pi_A and pi_B' are needed early); costs one more level
-uint32_t k_tile_entries(bool small = false);
+                    uint32_t L, uint32_t shift, uint32_t *Xo, uint32_t *Yo);
+// block-cooperative level: tile = T entries (power of two <= k_tile_entries()), grid (n_out, windows, X | Y blocks)
+uint32_t k_tile_entries();
 template <class F>
 void k_tile_reduce(stream_t s, uint32_t windows, const uint32_t *X, const uint32_t *Y1, const uint32_t *Y2, uint32_t n_in,
                    uint32_t n_out, uint32_t T, uint32_t shift, uint32_t *Xo, uint32_t *Y1o, uint32_t *Y2o);

@@ -30,9 +30,8 @@ void k_chunk_merge(stream_t s, size_t max_split, const uint32_t *split_list, con
 }
 template <class F>
 void k_reduce_level(stream_t s, size_t threads, const uint32_t *X, const uint32_t *Y, uint32_t n_in, uint32_t n_out,
-                    uint32_t L, uint32_t shift, uint32_t *Xo, uint32_t *Yo, bool small) {
-    if (small) launch<ReduceLevel<F, 32>>(threads, s, X, Y, n_in, n_out, L, shift, Xo, Yo);
-    else launch<ReduceLevel<F, 64>>(threads, s, X, Y, n_in, n_out, L, shift, Xo, Yo);
+                    uint32_t L, uint32_t shift, uint32_t *Xo, uint32_t *Yo) {
+    launch<ReduceLevel<F>>(threads, s, X, Y, n_in, n_out, L, shift, Xo, Yo);
 }
 template <class F>
 void k_tile_reduce(stream_t s, uint32_t windows, const uint32_t *X, const uint32_t *Y1, const uint32_t *Y2, uint32_t n_in,

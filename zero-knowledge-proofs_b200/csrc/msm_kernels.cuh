@@ -495,9 +495,9 @@ struct ChunkMergeSerial {
 //   Y'[g] = sum_j Y[gL + j] + 2^shift * sum_j j * X[gL + j]
 // With shift = log2(L) * level this telescopes to  sum_i i * X0[i] = Y_final[0]
 // (derivation in DESIGN.md "Bucket reduction").
-template <class F, int THREADS = 64>
+template <class F>
 struct ReduceLevel {
-    static constexpr int BLOCK = THREADS;   // 32: a block fits the registers one retiring accumulate block frees (prove schedule)
+    static constexpr int BLOCK = 64;
     G16_HD static void run(size_t t, const uint32_t *X, const uint32_t *Y, uint32_t n_in, uint32_t n_out, uint32_t L,
                            uint32_t shift, uint32_t *Xo, uint32_t *Yo) {
         uint32_t w = (uint32_t)(t / n_out), g = (uint32_t)(t % n_out);
@@ -543,7 +543,6 @@ struct ReduceLevel {
 // stride (conflict free for the quad-broadcast reads).
 constexpr int TILE_K = 4;        // consecutive entries folded serially by each element before the block scan
 constexpr int TILE_ELEMS = 64;   // elements (quads) per block -> 256 threads, TILE_K * TILE_ELEMS entries per tile
-constexpr int TILE_ELEMS_SMALL = 16;   // 64-thread blocks for a tail that has to run next to another MSM's accumulation
 #if !defined(G16_EMU) && defined(__CUDACC__)
 template <class F>
 __device__ __forceinline__ void tile_put(uint32_t *sm, int e, int q, const XYZZ<F> &p) {
