@@ -435,10 +435,11 @@ void prove_single_device(Context *c, const g16_pk *pk, const uint64_t *w, size_t
         copy_h2d(buf, w, num_vars * 32, LA.stream);
         d_w = buf;
     }
-    uint32_t *d_misc = LA.ws.prove_misc.as<uint32_t>(16 * 8 + 2 * AW1 + 4 * PW1 + AW1 + 64);
+    constexpr size_t AB1 = (2 * AW1 + 3) / 4 * 4;     // two affine records, padded: what follows is accessed 16 bytes at a time
+    uint32_t *d_misc = LA.ws.prove_misc.as<uint32_t>(16 * 8 + AB1 + 4 * PW1 + AW1 + 64);
     uint32_t *d_small = d_misc;                       // 16 scalars
     uint32_t *d_ab1 = d_misc + 16 * 8;                // pi_A and pi_B' affine records, back to back (inputs of the chains)
-    uint32_t *d_cparts = d_ab1 + 2 * AW1;             // 4 projective terms of pi_C: private part, H, s pi_A, r pi_B'
+    uint32_t *d_cparts = d_ab1 + AB1;                 // 4 projective terms of pi_C: private part, H, s pi_A, r pi_B'
     uint32_t *d_c_aff = d_cparts + 4 * PW1;           // pi_C affine
     copy_h2d(d_small, hs.data(), 16 * 32, LA.stream);
     for (Device *l : {&LB, &LB1, &LC}) stream_wait(l->stream, LA.stream);
