@@ -67,7 +67,16 @@ void k_partial_combine(stream_t s, const uint32_t *partials, uint32_t k, uint32_
 }
 template <class F>
 void k_scalar_mul_affine(stream_t s, size_t n, const uint32_t *scalars, const uint32_t *aff, uint32_t stride, uint32_t *out_xyzz) {
+#ifndef G16_EMU
+    for (size_t j0 = 0; j0 < n; j0 += 8) {   // eight chains per warp
+        uint32_t cnt = (uint32_t)std::min<size_t>(8, n - j0);
+        scalar_mul_quad_kernel<F><<<1, 32, 0, s>>>(cnt, scalars + j0 * 8, aff + j0 * stride, stride, out_xyzz + j0 * 4 * F::N);
+        G16_CUDA_CHECK(cudaGetLastError());
+        note_launch();
+    }
+#else
     launch<ScalarMulAffine<F>>(n, s, scalars, aff, stride, out_xyzz);
+#endif
 }
 template <class F>
 void k_precompute_bases(stream_t s, size_t n, const uint32_t *pts, uint32_t c, uint32_t nwin, uint32_t *table) {

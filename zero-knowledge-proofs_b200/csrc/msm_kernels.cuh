@@ -723,6 +723,46 @@ struct ScalarMulAffine {
     }
 };
 
+// The same on one warp with the 4-lane cooperative group law of quad.cuh (device build): quad j runs the chain of point
+// j (up to 8 points), two scalar bits per step from a table {P, 2P, 3P}: 128 steps of two doublings and one addition of
+// ~5.6 us each -- a thread on its own needs ~12 us per doubling or addition (measured: 445 operations in 5.3 ms,
+// profiles/r02_run15_prove_timeline_serial_chains.txt).
+#if !defined(G16_EMU) && defined(__CUDACC__)
+template <class F>
+__global__ void __launch_bounds__(32) scalar_mul_quad_kernel(uint32_t n, const uint32_t *scalars, const uint32_t *aff, uint32_t stride,
+                                                             uint32_t *out_xyzz) {
+    const uint32_t j = threadIdx.x >> 2;
+    const int q = threadIdx.x & 3;
+    const bool live = j < n;
+    uint32_t k[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    XYZZ<F> tab[3];
+    tab[0] = XYZZ<F>::inf();
+    if (live) {
+        load_scalar(scalars, j, true, k);
+        const uint32_t *src = aff + j * stride;
+        if (!src[2 * F::N]) {
+            uint32_t *dx = limbs(tab[0].x), *dy = limbs(tab[0].y);
+            for (int w = 0; w < F::N; ++w) { dx[w] = src[w]; dy[w] = src[F::N + w]; }
+            tab[0].zz = F::one(); tab[0].zzz = F::one();
+        }
+    }
+    tab[1] = tab[0]; xyzz_dbl_quad(tab[1], q);                      // 2P
+    tab[2] = tab[1]; xyzz_add_quad(tab[2], tab[0], q);              // 3P
+    XYZZ<F> acc = XYZZ<F>::inf();
+#pragma unroll 1
+    for (int bit = 254; bit >= 0; bit -= 2) {                       // pairs (255, 254), (253, 252), ... ; bit 255 is zero
+        xyzz_dbl_quad(acc, q);
+        xyzz_dbl_quad(acc, q);
+        uint32_t hi = bit + 1 < 256 ? (k[(bit + 1) >> 5] >> ((bit + 1) & 31)) & 1u : 0u;
+        uint32_t d = ((k[bit >> 5] >> (bit & 31)) & 1u) | (hi << 1);
+        XYZZ<F> t = XYZZ<F>::inf();
+        if (d) t = tab[d - 1];
+        xyzz_add_quad(acc, t, q);                                   // all quads step together; a zero digit adds infinity
+    }
+    if (live && q == 0) store_xyzz<F>(out_xyzz, j, acc);
+}
+#endif
+
 // Sum of k projective partial results (multi-GPU combine), then to affine.
 template <class F>
 struct PartialCombine {
