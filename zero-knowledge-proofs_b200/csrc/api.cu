@@ -455,24 +455,22 @@ void prove_single_device(Context *c, const g16_pk *pk, const uint64_t *w, size_t
     size_t na = std::min(num_vars, pk->a_len), nb2 = std::min(num_vars, pk->b2_len), nb1 = std::min(num_vars, pk->b1_len);
     uint32_t *t_priv = d_cparts, *t_h = d_cparts + PW1, *t_mul = d_cparts + 2 * PW1;
     uint32_t *oa = LA.ws.out.as<uint32_t>(PW1 + AW1) + PW1;
-    constexpr size_t NP = ~(size_t)0;   // (no host scalars in these calls)
-    constexpr bool SH = true;           // five MSMs share the GPU: lean reduction tails (engine.cuh, reduce_split)
-    msm_run<Fq>(LA, pk->a->shards[0], prefixed(LA, 0, 2, na), na + 2, true, co, nullptr, oa, 0, nullptr, NP, SH);
+    msm_run<Fq>(LA, pk->a->shards[0], prefixed(LA, 0, 2, na), na + 2, true, co, nullptr, oa);
     uint32_t *ob = LB.ws.out.as<uint32_t>(PW2 + AW2) + PW2;
-    msm_run<Fq2>(LB, pk->b2->shards[0], prefixed(LB, 2, 2, nb2), nb2 + 2, true, co, nullptr, ob, 0, nullptr, NP, SH);
+    msm_run<Fq2>(LB, pk->b2->shards[0], prefixed(LB, 2, 2, nb2), nb2 + 2, true, co, nullptr, ob);
     size_t nh = (h || (dev && dev->d_h)) ? std::min(num_h, pk->h_len) : 0;
     if (dev && dev->d_h) {
-        msm_run<Fq>(LH, pk->h->shards[0], dev->d_h, nh, true, co, t_h, nullptr, 0, nullptr, NP, SH);
+        msm_run<Fq>(LH, pk->h->shards[0], dev->d_h, nh, true, co, t_h, nullptr);
     } else {
         uint32_t *d_h = LH.ws.scalars.as<uint32_t>(nh * 8 + 8);
         copy_h2d(d_h, h, nh * 32, LH.stream);
-        msm_run<Fq>(LH, pk->h->shards[0], d_h, nh, true, co, t_h, nullptr, 0, nullptr, NP, SH);     // nh == 0 -> identity
+        msm_run<Fq>(LH, pk->h->shards[0], d_h, nh, true, co, t_h, nullptr);     // nh == 0 -> identity
     }
     uint32_t *ob1 = LB1.ws.out.as<uint32_t>(PW1 + AW1) + PW1;
-    msm_run<Fq>(LB1, pk->b1->shards[0], prefixed(LB1, 4, 1, nb1), nb1 + 1, true, co, nullptr, ob1, 0, nullptr, NP, SH);
+    msm_run<Fq>(LB1, pk->b1->shards[0], prefixed(LB1, 4, 1, nb1), nb1 + 1, true, co, nullptr, ob1);
     size_t first_priv = pk->num_public + 1;
     size_t nic = num_vars > first_priv ? std::min(num_vars - first_priv, pk->ic_len) : 0;
-    msm_run<Fq>(LC, pk->ic->shards[0], d_w + first_priv * 8, nic, true, co, t_priv, nullptr, 0, nullptr, NP, SH);
+    msm_run<Fq>(LC, pk->ic->shards[0], d_w + first_priv * 8, nic, true, co, t_priv, nullptr);
     // the rest of pi_C on lane 4 once pi_A, H and pi_B' exist (device-side dependency, no host wait)
     for (Device *l : {&LA, &LH, &LB1}) stream_wait(LC.stream, l->stream);
     copy_d2d(d_ab1, oa, AW1 * 4, LC.stream);
@@ -573,9 +571,8 @@ void prove_multi_device(Context *c, const g16_pk *pk, const uint64_t *w, size_t 
                     d_sc = d;
                 }
             }
-            // (five MSMs share each GPU: lean reduction tails, see reduce_split)
-            if (jb.g2) msm_run<Fq2>(ln, sh, d_sc, cnt, true, co, d_out, nullptr, lo[j] - std::min(lo[j], sh.begin), nullptr, ~(size_t)0, true);
-            else msm_run<Fq>(ln, sh, d_sc, cnt, true, co, d_out, nullptr, lo[j] - std::min(lo[j], sh.begin), nullptr, ~(size_t)0, true);
+            if (jb.g2) msm_run<Fq2>(ln, sh, d_sc, cnt, true, co, d_out, nullptr, lo[j] - std::min(lo[j], sh.begin));
+            else msm_run<Fq>(ln, sh, d_sc, cnt, true, co, d_out, nullptr, lo[j] - std::min(lo[j], sh.begin));
             copy_peer(part_of(j, k), d_out, PW * 4, ln.stream);
         }
     }

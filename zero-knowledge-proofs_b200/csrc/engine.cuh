@@ -249,14 +249,10 @@ constexpr unsigned ITEM_SHIFT = 17;
 #ifndef G16_RED_TILE_MAX_LOG2
 #define G16_RED_TILE_MAX_LOG2 15
 #endif
-// shared_gpu: the MSM runs next to others (prove schedule), where the GPU time a kernel OCCUPIES counts, not its latency:
-// a block-cooperative level over 2^15 entries holds 87 % of the GPU's registers for 0.3 ms (G1) / 1.1 ms (G2) while it
-// mostly waits on dependent multiplications, so the tree stays with the thread-level kernel (2 K-8 K threads, a few
-// per cent of the registers) down to 2^11 entries; alone, that costs ~0.1 ms of extra latency
-inline void reduce_split(size_t buckets, bool shared_gpu, size_t &tile_level_max, size_t &thread_level_groups) {
+inline void reduce_split(size_t buckets, size_t &tile_level_max, size_t &thread_level_groups) {
     bool big = buckets > ((size_t)1 << 20);
     thread_level_groups = (size_t)1 << (big ? 17 : G16_RED_GROUPS_LOG2);
-    tile_level_max = (size_t)1 << (shared_gpu ? 11 : big ? 16 : G16_RED_TILE_MAX_LOG2);
+    tile_level_max = (size_t)1 << (big ? 16 : G16_RED_TILE_MAX_LOG2);
 }
 
 // One MSM on one lane as three steps, so that a schedule of several MSMs (prove) can order them: `front` = stages 1-3
@@ -350,7 +346,7 @@ struct MsmJob {
     }
 
     // stages 5-6.  d_out_xyzz: 4 * FieldWords<F>::N words (may be null), d_out_aff: 2 * FieldWords<F>::N + 1 words (may be null)
-    void back(uint32_t *d_out_xyzz, uint32_t *d_out_aff, bool shared_gpu = false) {
+    void back(uint32_t *d_out_xyzz, uint32_t *d_out_aff) {
         stream_t s = dv.stream;
         Workspace &ws = dv.ws;
         dv.timer.mark(4, s);
@@ -362,7 +358,7 @@ struct MsmJob {
         int flip = 0;
         constexpr size_t PWORDS = 4 * FieldWords<F>::N;
         size_t TILE_LEVEL_MAX, THREAD_LEVEL_GROUPS;
-        reduce_split((size_t)plan.bwin * plan.nb, shared_gpu, TILE_LEVEL_MAX, THREAD_LEVEL_GROUPS);
+        reduce_split((size_t)plan.bwin * plan.nb, TILE_LEVEL_MAX, THREAD_LEVEL_GROUPS);
         while (n_in > 1) {
             uint32_t n_out, log_l;
             if ((size_t)plan.bwin * n_in > TILE_LEVEL_MAX) {
@@ -406,7 +402,7 @@ struct MsmJob {
 template <class F>
 void msm_run(Device &dv, const BasesShard &sh, const uint32_t *d_scalars, size_t n, bool mont, unsigned c_override,
              uint32_t *d_out_xyzz, uint32_t *d_out_aff, size_t first = 0, const uint64_t *h_scalars = nullptr,
-             size_t pipe_min = ~(size_t)0, bool shared_gpu = false) {
+             size_t pipe_min = ~(size_t)0) {
     stream_t s = dv.stream;
     if (n == 0) {
         k_partial_combine<F>(s, nullptr, 0u, d_out_xyzz, d_out_aff);
@@ -457,7 +453,7 @@ void msm_run(Device &dv, const BasesShard &sh, const uint32_t *d_scalars, size_t
         job.front(d_scalars + lo * 8, lo, cnt, mont, k == 0);
         job.accumulate(k > 0);   // later ranges continue the bucket sums of the earlier ones
     }
-    job.back(d_out_xyzz, d_out_aff, shared_gpu);
+    job.back(d_out_xyzz, d_out_aff);
 }
 
 // Import host points (ark layout + infinity bytes) into a device shard.
