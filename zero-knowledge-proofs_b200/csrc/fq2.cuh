@@ -27,9 +27,9 @@ struct Fq2 {
         Fq s = Fq::mul(Fq::add(a.c0, a.c1), Fq::add(b.c0, b.c1));
         return Fq2{Fq::sub(v0, v1), Fq::sub(Fq::sub(s, v0), v1)};
     }
-    G16_HD static Fq2 mul(const Fq2 &a, const Fq2 &b) { return mul_karatsuba(a, b); }
+    G16_FQ2_MUL_HD static Fq2 mul(const Fq2 &a, const Fq2 &b) { return mul_karatsuba(a, b); }
     // complex squaring: 2 Fq multiplications
-    G16_HD static Fq2 sqr(const Fq2 &a) {
+    G16_FQ2_MUL_HD static Fq2 sqr(const Fq2 &a) {
         Fq m = Fq::mul(a.c0, a.c1);
         Fq t = Fq::mul(Fq::add(a.c0, a.c1), Fq::sub(a.c0, a.c1));
         return Fq2{t, Fq::dbl(m)};

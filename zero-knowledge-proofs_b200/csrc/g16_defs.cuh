@@ -35,6 +35,16 @@
 #define G16_MUL_HD inline __attribute__((noinline))
 #endif
 
+// G2 kernels off the hot path (G16_COLD_FQ2 translation units: bucket reduction): the Fq multiplication stays inline
+// but the Fq2 multiplication / squaring (3 / 2 Fq multiplications, ~1000 instructions) become calls -- one copy of the
+// code instead of 40 per point addition, and the call overhead is spread over a thousand instructions instead of the
+// three hundred of an out-of-line Fq multiplication.
+#if defined(__CUDACC__) && defined(G16_COLD_FQ2)
+#define G16_FQ2_MUL_HD __host__ __device__ __noinline__
+#else
+#define G16_FQ2_MUL_HD G16_HD
+#endif
+
 namespace g16 {
 
 // ---------------------------------------------------------------------------------------

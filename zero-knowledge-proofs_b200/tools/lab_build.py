@@ -29,6 +29,9 @@ VARIANTS = {
     "g1_b128": {"k_acc_g1.cu": ["-DG16_ACC_BLOCK=128", "-DG16_ACC_MIN_BLOCKS_G1=3"]},
     "g1_b32_mb12": {"k_acc_g1.cu": ["-DG16_ACC_BLOCK=32", "-DG16_ACC_MIN_BLOCKS_G1=12"]},
     "g2_b128": {"k_acc_g2.cu": ["-DG16_ACC_BLOCK=128"]},
+    "g2_acc_fq2_calls": {"k_acc_g2.cu": ["-DG16_COLD_FQ2=1"]},
+    "g2_acc_fq2_calls_mb6": {"k_acc_g2.cu": ["-DG16_COLD_FQ2=1", "-DG16_ACC_MIN_BLOCKS_G2=6"]},
+    "g2_comb_fq2_calls": {"k_comb_g2.cu": ["-DG16_COLD_FQ2=1", "-UG16_COLD"]},
     "prove_no_split_tail": {"api.cu": ["-DG16_PROVE_SPLIT_TAIL=0"]},
     "item_floor8": engine("-DG16_ITEM_FLOOR=8"),
     "red_14_15": engine("-DG16_RED_GROUPS_LOG2=14"),
