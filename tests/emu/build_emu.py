@@ -28,7 +28,8 @@ def build(force: bool = False) -> str:
     for s in srcs:
         o = os.path.join(os.path.dirname(OUT), os.path.basename(s) + ".o")
         objs.append(o)
-        procs.append(subprocess.Popen(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-DG16_EMU=1", "-x", "c++", "-c", s, "-o", o]))
+        extra = os.environ.get("G16_EMU_EXTRA_FLAGS", "").split()   # A/B of compile-time variants (e.g. -DG16_FQ2_DUAL=1)
+        procs.append(subprocess.Popen(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-DG16_EMU=1"] + extra + ["-x", "c++", "-c", s, "-o", o]))
     for p in procs:
         if p.wait() != 0:
             raise RuntimeError("emu build failed")

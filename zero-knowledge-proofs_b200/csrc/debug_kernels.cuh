@@ -18,6 +18,7 @@ struct DebugFqOp {
             case 3: r = Fq::inv(x); break;
             case 4: r = Fq::sqr(x); break;
             case 5: r = Fq::neg(x); break;
+            case 6: r = Fq::mul_dual(x, y, Fq::sqr(x), Fq::add(x, y)); break;   // (x y + x^2 (x + y)) R^-1
             default: r = Fq::zero();
         }
         for (int j = 0; j < 12; ++j) out[12 * i + j] = r.l[j];

@@ -191,6 +191,92 @@ struct Fp {
         final_sub(r.l);
         return r;
     }
+    // ---- two products, one reduction:  (a x + a2 y) R^-1 mod p ---------------------------------------------------
+    // The same CIOS rounds with a second product term per round: 2 N^2 + N^2 + N wide MADs instead of the
+    // 2 (2 N^2 + N) of two multiplications, and the sum of the two products never exists as a 2N-word number -- the
+    // accumulator stays N + 1 words.  With a, a2 < p the result is below p (2p / R + 1) < 2p (p has three spare top
+    // bits), so one conditional subtraction restores the invariant.  Used for Fq2: c0 = a0 b0 + a1 (-b1),
+    // c1 = a0 b1 + a1 b0 (fq2.cuh, quad.cuh's lane-pair form).
+    template <bool FIRST>
+    G16_HD static void round2(uint32_t *E, uint32_t *O, const uint32_t *a, uint32_t bi, const uint32_t *a2, uint32_t bi2) {
+        if (FIRST) {
+#pragma unroll
+            for (int j = 0; j < N; j += 2) {
+                E[j] = mul_lo(a[j], bi);
+                E[j + 1] = mul_hi(a[j], bi);
+                O[j] = mul_lo(a[j + 1], bi);
+                O[j + 1] = mul_hi(a[j + 1], bi);
+            }
+        } else {
+            E[0] = add_cc(E[0], O[1]);
+#pragma unroll
+            for (int j = 0; j < N - 2; j += 2) {
+                O[j] = madc_lo_cc(a[j + 1], bi, O[j + 2]);
+                O[j + 1] = madc_hi_cc(a[j + 1], bi, O[j + 3]);
+            }
+            O[N - 2] = madc_lo_cc(a[N - 1], bi, 0u);
+            O[N - 1] = madc_hi(a[N - 1], bi, 0u);
+            E[0] = mad_lo_cc(a[0], bi, E[0]);
+            E[1] = madc_hi_cc(a[0], bi, E[1]);
+#pragma unroll
+            for (int j = 2; j < N; j += 2) {
+                E[j] = madc_lo_cc(a[j], bi, E[j]);
+                E[j + 1] = madc_hi_cc(a[j], bi, E[j + 1]);
+            }
+            O[N - 1] = addc(O[N - 1], 0u);
+        }
+        // second product term on the same columns (the running value stays below 3p 2^32: no carry leaves O[N-1])
+        O[0] = mad_lo_cc(a2[1], bi2, O[0]);
+        O[1] = madc_hi_cc(a2[1], bi2, O[1]);
+#pragma unroll
+        for (int j = 2; j < N - 2; j += 2) {
+            O[j] = madc_lo_cc(a2[j + 1], bi2, O[j]);
+            O[j + 1] = madc_hi_cc(a2[j + 1], bi2, O[j + 1]);
+        }
+        O[N - 2] = madc_lo_cc(a2[N - 1], bi2, O[N - 2]);
+        O[N - 1] = madc_hi(a2[N - 1], bi2, O[N - 1]);
+        E[0] = mad_lo_cc(a2[0], bi2, E[0]);
+        E[1] = madc_hi_cc(a2[0], bi2, E[1]);
+#pragma unroll
+        for (int j = 2; j < N; j += 2) {
+            E[j] = madc_lo_cc(a2[j], bi2, E[j]);
+            E[j + 1] = madc_hi_cc(a2[j], bi2, E[j + 1]);
+        }
+        O[N - 1] = addc(O[N - 1], 0u);
+        uint32_t m = E[0] * P::NINV;
+        O[0] = mad_lo_cc(P::MOD(1), m, O[0]);
+        O[1] = madc_hi_cc(P::MOD(1), m, O[1]);
+#pragma unroll
+        for (int j = 2; j < N; j += 2) {
+            O[j] = madc_lo_cc(P::MOD(j + 1), m, O[j]);
+            O[j + 1] = madc_hi_cc(P::MOD(j + 1), m, O[j + 1]);
+        }
+        E[0] = mad_lo_cc(P::MOD(0), m, E[0]);
+        E[1] = madc_hi_cc(P::MOD(0), m, E[1]);
+#pragma unroll
+        for (int j = 2; j < N; j += 2) {
+            E[j] = madc_lo_cc(P::MOD(j), m, E[j]);
+            E[j + 1] = madc_hi_cc(P::MOD(j), m, E[j + 1]);
+        }
+        O[N - 1] = addc(O[N - 1], 0u);
+    }
+    G16_MUL_HD static Fp mul_dual(const Fp &a, const Fp &x, const Fp &a2, const Fp &y) {
+        uint32_t ev[N], od[N];
+        round2<true>(ev, od, a.l, x.l[0], a2.l, y.l[0]);
+        round2<false>(od, ev, a.l, x.l[1], a2.l, y.l[1]);
+#pragma unroll
+        for (int i = 2; i < N; i += 2) {
+            round2<false>(ev, od, a.l, x.l[i], a2.l, y.l[i]);
+            round2<false>(od, ev, a.l, x.l[i + 1], a2.l, y.l[i + 1]);
+        }
+        Fp r;
+        r.l[0] = add_cc(ev[0], od[1]);
+#pragma unroll
+        for (int i = 1; i < N - 1; ++i) r.l[i] = addc_cc(ev[i], od[i + 1]);
+        r.l[N - 1] = addc(ev[N - 1], 0u);
+        final_sub(r.l);
+        return r;
+    }
     // A dedicated squaring (fewer IMAD.WIDE, longer dependent structure) was measured 5 % slower inside the bucket
     // kernel (profiles/README.md run 7); it lives in experiments/fp_wide.cuh, not in the library.
     G16_HD static Fp sqr(const Fp &a) { return mul(a, a); }

@@ -27,7 +27,19 @@ struct Fq2 {
         Fq s = Fq::mul(Fq::add(a.c0, a.c1), Fq::add(b.c0, b.c1));
         return Fq2{Fq::sub(v0, v1), Fq::sub(Fq::sub(s, v0), v1)};
     }
-    G16_FQ2_MUL_HD static Fq2 mul(const Fq2 &a, const Fq2 &b) { return mul_karatsuba(a, b); }
+    // schoolbook with two products per reduction (Fp::mul_dual): 2 x (2 products + 1 reduction) = 888 wide MADs against
+    // Karatsuba's 900, one negation instead of five Fq additions / subtractions, no v0 / v1 / s temporaries
+    G16_HD static Fq2 mul_dual(const Fq2 &a, const Fq2 &b) {
+        Fq nb1 = Fq::neg(b.c1);
+        return Fq2{Fq::mul_dual(a.c0, b.c0, a.c1, nb1), Fq::mul_dual(a.c0, b.c1, a.c1, b.c0)};
+    }
+    // Shipped: the two-product form (G2 accumulate at 2^20: 14.4 ms against 16.9 ms with Karatsuba on one box,
+    // profiles/r02_run20_lab_g2_pair_and_dual.txt; 92 bytes of spills instead of 328).  -DG16_FQ2_DUAL=0 builds the
+    // Karatsuba form for A/B runs (tools/lab_build.py).
+#ifndef G16_FQ2_DUAL
+#define G16_FQ2_DUAL 1
+#endif
+    G16_FQ2_MUL_HD static Fq2 mul(const Fq2 &a, const Fq2 &b) { return G16_FQ2_DUAL ? mul_dual(a, b) : mul_karatsuba(a, b); }
     // complex squaring: 2 Fq multiplications
     G16_FQ2_MUL_HD static Fq2 sqr(const Fq2 &a) {
         Fq m = Fq::mul(a.c0, a.c1);

@@ -4,12 +4,25 @@
 #include "kernel_api.cuh"
 #include "fixed_base_kernels.cuh"
 #include "msm_kernels.cuh"
+#include "pair_g2.cuh"
+#include <type_traits>
 
 namespace g16 {
 
 template <class F>
 void k_accumulate(stream_t s, size_t max_items, const uint32_t *pts, const uint32_t *entries, const WorkItem *work,
                   const uint32_t *n_items, uint32_t *buckets, uint32_t *chunk_out, bool add_to) {
+#if !defined(G16_EMU) && !G16_G2_ACC_THREAD
+    if constexpr (std::is_same<F, Fq2>::value) {   // G2 on the device: one lane pair per work item (pair_g2.cuh)
+        if (max_items == 0) return;
+        unsigned blocks = (unsigned)((2 * max_items + G16_PAIR_BLOCK - 1) / G16_PAIR_BLOCK);
+        if (add_to) accumulate_pair_g2_kernel<true><<<blocks, G16_PAIR_BLOCK, 0, s>>>(pts, entries, work, n_items, buckets, chunk_out);
+        else accumulate_pair_g2_kernel<false><<<blocks, G16_PAIR_BLOCK, 0, s>>>(pts, entries, work, n_items, buckets, chunk_out);
+        G16_CUDA_CHECK(cudaGetLastError());
+        note_launch();
+        return;
+    }
+#endif
     if (add_to) launch<BucketAccumulate<F, true>>(max_items, s, pts, entries, work, n_items, buckets, chunk_out);
     else launch<BucketAccumulate<F, false>>(max_items, s, pts, entries, work, n_items, buckets, chunk_out);
 }

@@ -26,6 +26,8 @@ def main():
     ap.add_argument("--log-n", type=int, default=22)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--cpu-sample", type=int, default=1 << 13)
+    ap.add_argument("--lib", default=None, help="alternative build of the library (A/B experiments)")
+    ap.add_argument("--groups", default="g1,g2")
     a = ap.parse_args()
     import torch
     import bls12_381 as bls
@@ -34,12 +36,14 @@ def main():
     oracle.build()
     n = 1 << a.log_n
     dev = torch.device("cuda:0")
-    ctx = groth16_cuda.Context([0])
+    ctx = groth16_cuda.Context([0], lib_path=a.lib)
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
     gens = {"g1": np.array(bls.g1_to_mont(bls.G1_GEN)[0], dtype=np.uint64),
             "g2": np.array(bls.g2_to_mont(bls.G2_GEN)[0], dtype=np.uint64)}
     th = oracle.max_threads()
     for group, width in (("g1", 24), ("g2", 48)):
+        if group not in a.groups.split(","):
+            continue
         for dist, bits in (("ref_faithful_u64", 64), ("full_width", 255)):
             k = oracle.gen_scalars(0x5e70 + bits, n, bits)
             d_k = torch.from_numpy(k.view(np.int64)).to(dev)

@@ -31,6 +31,14 @@ VARIANTS = {
     "g2_b128": {"k_acc_g2.cu": ["-DG16_ACC_BLOCK=128"]},
     "g2_acc_fq2_calls": {"k_acc_g2.cu": ["-DG16_COLD_FQ2=1"]},
     "g2_acc_fq2_calls_mb6": {"k_acc_g2.cu": ["-DG16_COLD_FQ2=1", "-DG16_ACC_MIN_BLOCKS_G2=6"]},
+    # G2 accumulate on lane pairs (csrc/pair_g2.cuh) instead of one thread per item; Karatsuba instead of the two-product Fq2 multiplication
+    "g2_pair": {"k_acc_g2.cu": ["-DG16_G2_ACC_THREAD=0"]},
+    "g2_pair_mb4": {"k_acc_g2.cu": ["-DG16_G2_ACC_THREAD=0", "-DG16_PAIR_MIN_BLOCKS=4"]},
+    "g2_acc_karatsuba": {"k_acc_g2.cu": ["-DG16_FQ2_DUAL=0"]},
+    "g2_red_dual": {"k_red_g2.cu": ["-UG16_FQ2_DUAL", "-DG16_FQ2_DUAL=1"]},
+    "g2_fb_karatsuba": {"k_fbmul_g2.cu": ["-DG16_FQ2_DUAL=0"], "k_fbtab_g2.cu": ["-DG16_FQ2_DUAL=0"]},
+    "g2_pre_karatsuba": {"k_pre_g2.cu": ["-DG16_FQ2_DUAL=0"]},
+    "g2_comb_karatsuba": {"k_comb_g2.cu": ["-DG16_FQ2_DUAL=0"]},
     "g2_comb_fq2_calls": {"k_comb_g2.cu": ["-DG16_COLD_FQ2=1", "-UG16_COLD"]},
     "prove_no_split_tail": {"api.cu": ["-DG16_PROVE_SPLIT_TAIL=0"]},
     "item_floor8": engine("-DG16_ITEM_FLOOR=8"),
@@ -54,7 +62,7 @@ def build_variant(name, units):
             stats = [l for l in res.stdout.splitlines() if "BucketAccumulate" in l or "Used" in l or "spill" in l]
             # the lines that follow the BucketAccumulate entry
             for i, l in enumerate(res.stdout.splitlines()):
-                if "Compiling entry function" in l and "BucketAccumulate" in l:
+                if "Compiling entry function" in l and ("BucketAccumulate" in l or "accumulate_pair" in l):
                     print(f"[{name}]", " | ".join(x.strip() for x in res.stdout.splitlines()[i + 2:i + 4]))
             objs.append(obj)
         else:
