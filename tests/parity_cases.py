@@ -138,6 +138,11 @@ def check_debug_field(ctx, oracle, n=2000):
     # two products, one reduction (Fp::mul_dual): (x y + x^2 (x + y)) R^-1
     assert lib.g16_debug_fq_op(ctx.handle, 6, a.ctypes.data, b.ctypes.data, out.ctypes.data, a.shape[0]) == 0
     assert (out == oracle.fq_add(oracle.fq_mul(a, b), oracle.fq_mul(oracle.fq_mul(a, a), oracle.fq_add(a, b)))).all()
+    xy, x2s = oracle.fq_mul(a, b), oracle.fq_mul(oracle.fq_mul(a, a), oracle.fq_add(a, b))
+    assert lib.g16_debug_fq_op(ctx.handle, 7, a.ctypes.data, b.ctypes.data, out.ctypes.data, a.shape[0]) == 0   # four products
+    assert (out == oracle.fq_sub(oracle.fq_add(oracle.fq_add(xy, x2s), oracle.fq_mul(b, b)), oracle.fq_mul(a, a))).all()
+    assert lib.g16_debug_fq_op(ctx.handle, 8, a.ctypes.data, b.ctypes.data, out.ctypes.data, a.shape[0]) == 0   # difference of products
+    assert (out == oracle.fq_sub(xy, x2s)).all()
     nz = a[a.any(axis=1)][:64]
     outi = np.zeros_like(nz)
     assert lib.g16_debug_fq_op(ctx.handle, 3, nz.ctypes.data, None, outi.ctypes.data, nz.shape[0]) == 0

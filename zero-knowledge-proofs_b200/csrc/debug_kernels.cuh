@@ -19,6 +19,8 @@ struct DebugFqOp {
             case 4: r = Fq::sqr(x); break;
             case 5: r = Fq::neg(x); break;
             case 6: r = Fq::mul_dual(x, y, Fq::sqr(x), Fq::add(x, y)); break;   // (x y + x^2 (x + y)) R^-1
+            case 7: r = Fq::mul_quad(x, y, Fq::sqr(x), Fq::add(x, y), y, y, Fq::neg(x), x); break;   // ... + y^2 - x^2
+            case 8: r = Fq::mul_diff(x, y, Fq::sqr(x), Fq::add(x, y)); break;   // x y - x^2 (x + y)
             default: r = Fq::zero();
         }
         for (int j = 0; j < 12; ++j) out[12 * i + j] = r.l[j];

@@ -47,7 +47,7 @@ G16_HD XYZZ<F> xyzz_mdbl(const F &x2, const F &y2) {
     F m = F::add(F::dbl(xx), xx);
     XYZZ<F> r;
     r.x = F::sub(F::sqr(m), F::dbl(s));
-    r.y = F::sub(F::mul(m, F::sub(s, r.x)), F::mul(w, y2));
+    r.y = F::mul_diff(m, F::sub(s, r.x), w, y2);
     r.zz = v;
     r.zzz = w;
     return r;
@@ -74,7 +74,7 @@ G16_HD void xyzz_madd(XYZZ<F> &acc, const F &x2, const F &y2) {
     F ppp = F::mul(p, pp);
     F q = F::mul(acc.x, pp);
     F x3 = F::sub(F::sub(F::sqr(r), ppp), F::dbl(q));
-    acc.y = F::sub(F::mul(r, F::sub(q, x3)), F::mul(acc.y, ppp));
+    acc.y = F::mul_diff(r, F::sub(q, x3), acc.y, ppp);
     acc.x = x3;
     acc.zz = F::mul(acc.zz, pp);
     acc.zzz = F::mul(acc.zzz, ppp);
@@ -91,7 +91,7 @@ G16_HD void xyzz_dbl(XYZZ<F> &acc) {
     F xx = F::sqr(acc.x);
     F m = F::add(F::dbl(xx), xx);
     F x3 = F::sub(F::sqr(m), F::dbl(s));
-    acc.y = F::sub(F::mul(m, F::sub(s, x3)), F::mul(w, acc.y));
+    acc.y = F::mul_diff(m, F::sub(s, x3), w, acc.y);
     acc.x = x3;
     acc.zz = F::mul(v, acc.zz);
     acc.zzz = F::mul(w, acc.zzz);
@@ -117,7 +117,7 @@ G16_HD void xyzz_add(XYZZ<F> &acc, const XYZZ<F> &b) {
     F ppp = F::mul(p, pp);
     F q = F::mul(u1, pp);
     F x3 = F::sub(F::sub(F::sqr(r), ppp), F::dbl(q));
-    acc.y = F::sub(F::mul(r, F::sub(q, x3)), F::mul(s1, ppp));
+    acc.y = F::mul_diff(r, F::sub(q, x3), s1, ppp);
     acc.x = x3;
     acc.zz = F::mul(F::mul(acc.zz, b.zz), pp);
     acc.zzz = F::mul(F::mul(acc.zzz, b.zzz), ppp);

@@ -191,14 +191,36 @@ struct Fp {
         final_sub(r.l);
         return r;
     }
-    // ---- two products, one reduction:  (a x + a2 y) R^-1 mod p ---------------------------------------------------
-    // The same CIOS rounds with a second product term per round: 2 N^2 + N^2 + N wide MADs instead of the
-    // 2 (2 N^2 + N) of two multiplications, and the sum of the two products never exists as a 2N-word number -- the
-    // accumulator stays N + 1 words.  With a, a2 < p the result is below p (2p / R + 1) < 2p (p has three spare top
-    // bits), so one conditional subtraction restores the invariant.  Used for Fq2: c0 = a0 b0 + a1 (-b1),
-    // c1 = a0 b1 + a1 b0 (fq2.cuh, quad.cuh's lane-pair form).
+    // ---- K products, one reduction:  (sum_k a_k x_k) R^-1 mod p --------------------------------------------------
+    // The same CIOS rounds with K product terms per round: (K + 1) N^2 + N wide MADs instead of the K (2 N^2 + N) of
+    // K multiplications, and the sum of the products never exists as a 2N-word number -- the accumulator stays N + 1
+    // words (the running value is below (K + 1) p 2^32 < 2^(32 N + 32) for K <= 4: p has three spare top bits).  With
+    // all a_k < p the result is below p (K p / R + 1) < 2p for K <= 4, so one conditional subtraction restores the
+    // invariant.  Uses: Fq2 products c0 = a0 b0 + a1 (-b1), c1 = a0 b1 + a1 b0 (fq2.cuh), and the y coordinate of every
+    // group addition, y3 = r (q - x3) - y1 ppp (ec.cuh): one reduction saved each time.
+    // term k of one round: value += a * bi on the split accumulator (E, O), continuing a value already in place
+    G16_HD static void round_term(uint32_t *E, uint32_t *O, const uint32_t *a, uint32_t bi) {
+        O[0] = mad_lo_cc(a[1], bi, O[0]);
+        O[1] = madc_hi_cc(a[1], bi, O[1]);
+#pragma unroll
+        for (int j = 2; j < N - 2; j += 2) {
+            O[j] = madc_lo_cc(a[j + 1], bi, O[j]);
+            O[j + 1] = madc_hi_cc(a[j + 1], bi, O[j + 1]);
+        }
+        O[N - 2] = madc_lo_cc(a[N - 1], bi, O[N - 2]);
+        O[N - 1] = madc_hi(a[N - 1], bi, O[N - 1]);   // no carry leaves O[N-1] (bound above)
+        E[0] = mad_lo_cc(a[0], bi, E[0]);
+        E[1] = madc_hi_cc(a[0], bi, E[1]);
+#pragma unroll
+        for (int j = 2; j < N; j += 2) {
+            E[j] = madc_lo_cc(a[j], bi, E[j]);
+            E[j + 1] = madc_hi_cc(a[j], bi, E[j + 1]);
+        }
+        O[N - 1] = addc(O[N - 1], 0u);
+    }
+    // first term of a round (merges the shift of the previous round's O, as `round` does) ...
     template <bool FIRST>
-    G16_HD static void round2(uint32_t *E, uint32_t *O, const uint32_t *a, uint32_t bi, const uint32_t *a2, uint32_t bi2) {
+    G16_HD static void round_open(uint32_t *E, uint32_t *O, const uint32_t *a, uint32_t bi) {
         if (FIRST) {
 #pragma unroll
             for (int j = 0; j < N; j += 2) {
@@ -225,24 +247,9 @@ struct Fp {
             }
             O[N - 1] = addc(O[N - 1], 0u);
         }
-        // second product term on the same columns (the running value stays below 3p 2^32: no carry leaves O[N-1])
-        O[0] = mad_lo_cc(a2[1], bi2, O[0]);
-        O[1] = madc_hi_cc(a2[1], bi2, O[1]);
-#pragma unroll
-        for (int j = 2; j < N - 2; j += 2) {
-            O[j] = madc_lo_cc(a2[j + 1], bi2, O[j]);
-            O[j + 1] = madc_hi_cc(a2[j + 1], bi2, O[j + 1]);
-        }
-        O[N - 2] = madc_lo_cc(a2[N - 1], bi2, O[N - 2]);
-        O[N - 1] = madc_hi(a2[N - 1], bi2, O[N - 1]);
-        E[0] = mad_lo_cc(a2[0], bi2, E[0]);
-        E[1] = madc_hi_cc(a2[0], bi2, E[1]);
-#pragma unroll
-        for (int j = 2; j < N; j += 2) {
-            E[j] = madc_lo_cc(a2[j], bi2, E[j]);
-            E[j + 1] = madc_hi_cc(a2[j], bi2, E[j + 1]);
-        }
-        O[N - 1] = addc(O[N - 1], 0u);
+    }
+    // ... and the reduction step that closes it: on exit E[0] == 0 (mod 2^32) and the caller swaps roles
+    G16_HD static void round_close(uint32_t *E, uint32_t *O) {
         uint32_t m = E[0] * P::NINV;
         O[0] = mad_lo_cc(P::MOD(1), m, O[0]);
         O[1] = madc_hi_cc(P::MOD(1), m, O[1]);
@@ -260,14 +267,23 @@ struct Fp {
         }
         O[N - 1] = addc(O[N - 1], 0u);
     }
-    G16_MUL_HD static Fp mul_dual(const Fp &a, const Fp &x, const Fp &a2, const Fp &y) {
+    template <bool FIRST, int K>
+    G16_HD static void round_sum(uint32_t *E, uint32_t *O, const Fp *const *a, const Fp *const *x, int i) {
+        round_open<FIRST>(E, O, a[0]->l, x[0]->l[i]);
+#pragma unroll
+        for (int k = 1; k < K; ++k) round_term(E, O, a[k]->l, x[k]->l[i]);
+        round_close(E, O);
+    }
+    template <int K>
+    G16_HD static Fp mul_sum(const Fp *const *a, const Fp *const *x) {
+        static_assert(K >= 1 && K <= 4, "the one-subtraction bound holds up to four products");
         uint32_t ev[N], od[N];
-        round2<true>(ev, od, a.l, x.l[0], a2.l, y.l[0]);
-        round2<false>(od, ev, a.l, x.l[1], a2.l, y.l[1]);
+        round_sum<true, K>(ev, od, a, x, 0);
+        round_sum<false, K>(od, ev, a, x, 1);
 #pragma unroll
         for (int i = 2; i < N; i += 2) {
-            round2<false>(ev, od, a.l, x.l[i], a2.l, y.l[i]);
-            round2<false>(od, ev, a.l, x.l[i + 1], a2.l, y.l[i + 1]);
+            round_sum<false, K>(ev, od, a, x, i);
+            round_sum<false, K>(od, ev, a, x, i + 1);
         }
         Fp r;
         r.l[0] = add_cc(ev[0], od[1]);
@@ -276,6 +292,25 @@ struct Fp {
         r.l[N - 1] = addc(ev[N - 1], 0u);
         final_sub(r.l);
         return r;
+    }
+    // a x + a2 y
+    G16_MUL_HD static Fp mul_dual(const Fp &a, const Fp &x, const Fp &a2, const Fp &y) {
+        const Fp *as[2] = {&a, &a2}, *xs[2] = {&x, &y};
+        return mul_sum<2>(as, xs);
+    }
+    // a x + a2 y + a3 z + a4 w
+    G16_MUL_HD static Fp mul_quad(const Fp &a, const Fp &x, const Fp &a2, const Fp &y, const Fp &a3, const Fp &z,
+                                  const Fp &a4, const Fp &w) {
+        const Fp *as[4] = {&a, &a2, &a3, &a4}, *xs[4] = {&x, &y, &z, &w};
+        return mul_sum<4>(as, xs);
+    }
+    // a x - b y  (the y coordinate of the group additions); same interface on Fq2
+    // (-DG16_MUL_DIFF=0 builds the two-multiplication form for A/B runs, tools/lab_build.py)
+#ifndef G16_MUL_DIFF
+#define G16_MUL_DIFF 1
+#endif
+    G16_HD static Fp mul_diff(const Fp &a, const Fp &x, const Fp &b, const Fp &y) {
+        return G16_MUL_DIFF ? mul_dual(a, x, neg(b), y) : sub(mul(a, x), mul(b, y));
     }
     // A dedicated squaring (fewer IMAD.WIDE, longer dependent structure) was measured 5 % slower inside the bucket
     // kernel (profiles/README.md run 7); it lives in experiments/fp_wide.cuh, not in the library.

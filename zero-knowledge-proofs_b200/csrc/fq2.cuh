@@ -36,10 +36,36 @@ struct Fq2 {
     // Shipped: the two-product form (G2 accumulate at 2^20: 14.4 ms against 16.9 ms with Karatsuba on one box,
     // profiles/r02_run20_lab_g2_pair_and_dual.txt; 92 bytes of spills instead of 328).  -DG16_FQ2_DUAL=0 builds the
     // Karatsuba form for A/B runs (tools/lab_build.py).
+    // In the cold translation units (G16_COLD: the Fq multiplication is an out-of-line call) the multi-product forms
+    // lose -- their four / eight operands travel through local memory: G2 fixed-base 39 -> 29 M points/s, G2 precompute
+    // 372 -> 527 ms with the four-product y3 (profiles/r02_run22_*) -- so those units keep Karatsuba unless they say
+    // otherwise (k_pre_g2.cu: two-product multiplication yes, four-product y3 no).
 #ifndef G16_FQ2_DUAL
+#ifdef G16_COLD
+#define G16_FQ2_DUAL 0
+#else
 #define G16_FQ2_DUAL 1
 #endif
+#endif
+#ifndef G16_FQ2_QUAD   // y3 of the group additions as two four-product multiplications (mul_diff below)
+#ifdef G16_COLD
+#define G16_FQ2_QUAD 0
+#else
+#define G16_FQ2_QUAD G16_FQ2_DUAL
+#endif
+#endif
     G16_FQ2_MUL_HD static Fq2 mul(const Fq2 &a, const Fq2 &b) { return G16_FQ2_DUAL ? mul_dual(a, b) : mul_karatsuba(a, b); }
+    // a x - b y: four products and one reduction per component
+    //   c0 = a0 x0 - a1 x1 - b0 y0 + b1 y1,   c1 = a0 x1 + a1 x0 - b0 y1 - b1 y0
+    G16_HD static Fq2 mul_diff(const Fq2 &a, const Fq2 &x, const Fq2 &b, const Fq2 &y) {
+#if G16_FQ2_QUAD && G16_MUL_DIFF
+        Fq nx1 = Fq::neg(x.c1), nb0 = Fq::neg(b.c0), nb1 = Fq::neg(b.c1);
+        return Fq2{Fq::mul_quad(a.c0, x.c0, a.c1, nx1, nb0, y.c0, b.c1, y.c1),
+                   Fq::mul_quad(a.c0, x.c1, a.c1, x.c0, nb0, y.c1, nb1, y.c0)};
+#else
+        return sub(mul(a, x), mul(b, y));
+#endif
+    }
     // complex squaring: 2 Fq multiplications
     G16_FQ2_MUL_HD static Fq2 sqr(const Fq2 &a) {
         Fq m = Fq::mul(a.c0, a.c1);

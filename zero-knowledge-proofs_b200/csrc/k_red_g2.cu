@@ -3,6 +3,7 @@
 // against 5.29 ms at 2^19 buckets, profiles/r02_run21_lab_g2_dual_per_kernel.txt)
 #define G16_COLD_FQ2 1
 #define G16_FQ2_DUAL 0
+#define G16_FQ2_QUAD 0
 #include "kernel_impl.cuh"
 namespace g16 {
 template void k_tile_reduce<Fq2>(stream_t, uint32_t, const uint32_t *, const uint32_t *, const uint32_t *, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t *, uint32_t *, uint32_t *);

@@ -495,9 +495,13 @@ struct ChunkMergeSerial {
 //   Y'[g] = sum_j Y[gL + j] + 2^shift * sum_j j * X[gL + j]
 // With shift = log2(L) * level this telescopes to  sum_i i * X0[i] = Y_final[0]
 // (derivation in DESIGN.md "Bucket reduction").
+#ifndef G16_RED_MIN_BLOCKS_G2
+#define G16_RED_MIN_BLOCKS_G2 1   // left to ptxas (255 registers); A/B builds: tools/lab_build.py
+#endif
 template <class F>
 struct ReduceLevel {
     static constexpr int BLOCK = 64;
+    static constexpr int MIN_BLOCKS = F::N == 12 ? 1 : G16_RED_MIN_BLOCKS_G2;
     G16_HD static void run(size_t t, const uint32_t *X, const uint32_t *Y, uint32_t n_in, uint32_t n_out, uint32_t L,
                            uint32_t shift, uint32_t *Xo, uint32_t *Yo) {
         uint32_t w = (uint32_t)(t / n_out), g = (uint32_t)(t % n_out);

@@ -32,13 +32,18 @@ VARIANTS = {
     "g2_acc_fq2_calls": {"k_acc_g2.cu": ["-DG16_COLD_FQ2=1"]},
     "g2_acc_fq2_calls_mb6": {"k_acc_g2.cu": ["-DG16_COLD_FQ2=1", "-DG16_ACC_MIN_BLOCKS_G2=6"]},
     # G2 accumulate on lane pairs (csrc/pair_g2.cuh) instead of one thread per item; Karatsuba instead of the two-product Fq2 multiplication
+    # y3 = r (q - x3) - y1 ppp as two multiplications instead of one two- / four-product multiplication
+    "g1_acc_no_mul_diff": {"k_acc_g1.cu": ["-DG16_MUL_DIFF=0"]},
+    "g2_acc_no_mul_diff": {"k_acc_g2.cu": ["-DG16_MUL_DIFF=0"]},
     "g2_pair": {"k_acc_g2.cu": ["-DG16_G2_ACC_THREAD=0"]},
     "g2_pair_mb4": {"k_acc_g2.cu": ["-DG16_G2_ACC_THREAD=0", "-DG16_PAIR_MIN_BLOCKS=4"]},
     "g2_acc_karatsuba": {"k_acc_g2.cu": ["-DG16_FQ2_DUAL=0"]},
     "g2_red_dual": {"k_red_g2.cu": ["-UG16_FQ2_DUAL", "-DG16_FQ2_DUAL=1"]},
-    "g2_fb_karatsuba": {"k_fbmul_g2.cu": ["-DG16_FQ2_DUAL=0"], "k_fbtab_g2.cu": ["-DG16_FQ2_DUAL=0"]},
-    "g2_pre_karatsuba": {"k_pre_g2.cu": ["-DG16_FQ2_DUAL=0"]},
-    "g2_comb_karatsuba": {"k_comb_g2.cu": ["-DG16_FQ2_DUAL=0"]},
+    "g2_red_mb6": {"k_red_g2.cu": ["-DG16_RED_MIN_BLOCKS_G2=6"]},
+    "g2_red_mb8": {"k_red_g2.cu": ["-DG16_RED_MIN_BLOCKS_G2=8"]},
+    "g2_red_mb12": {"k_red_g2.cu": ["-DG16_RED_MIN_BLOCKS_G2=12"]},
+    "g2_fb_dual": {"k_fbmul_g2.cu": ["-DG16_FQ2_DUAL=1"], "k_fbtab_g2.cu": ["-DG16_FQ2_DUAL=1"]},
+    "g2_fb_inline": {"k_fbmul_g2.cu": ["-UG16_COLD"]},
     "g2_comb_fq2_calls": {"k_comb_g2.cu": ["-DG16_COLD_FQ2=1", "-UG16_COLD"]},
     "prove_no_split_tail": {"api.cu": ["-DG16_PROVE_SPLIT_TAIL=0"]},
     "item_floor8": engine("-DG16_ITEM_FLOOR=8"),
