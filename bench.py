@@ -46,6 +46,7 @@ import numpy as np  # noqa: E402
 # algorithmic work per (scalar, point) pair fixed by SURVEY.md 8(d): 16 windows x (8M + 2S) = 160 Fq
 # multiplications, 600 32-bit IMAD issues each
 FQ_MUL_PER_PAIR = 160
+FQ_MUL_PER_MADD = (8 * 300 + 444) / 300.0   # executed: 8 M + (2 products, 1 reduction), in units of one 300-MAD multiplication
 IMAD_PER_FQ_MUL = 600
 SEED_POINTS, SEED_SCALARS = 0xba5e0000, 0x5eed0000
 L2_BYTES = 126 << 20
@@ -618,10 +619,12 @@ def main():
                         "precomputed table lets the kernel run ceil(256/c) windows (see `executed`); the table costs "
                         f"{pre_ms:.0f} ms once and {-(-256 // max(pre_bits, 1)) * n_loc * 96 / 1e9:.1f} GB per GPU, outside the timed region")
     if acc_ms and (peak or {}).get("fq_mul_per_s"):
-        # what the kernel actually executes: one XYZZ mixed addition (8M + 2S) per non-zero digit, against the
-        # measured throughput of the engine's own Fq multiplication (lib/imad_peak)
-        ex = float(n_loc) * float(plan[1]) * 10.0 / (acc_ms * 1e-3)
-        roof["executed"] = {"fq_mul_per_pair": int(plan[1]) * 10, "fq_mul_per_s": ex,
+        # what the kernel actually executes: one XYZZ mixed addition per non-zero digit = 8 multiplications + one
+        # two-product multiplication for y3 (two products, one reduction: 444 of the 600 wide MADs of two
+        # multiplications) = 9.48 multiplication equivalents, against the measured throughput of the engine's own Fq
+        # multiplication (lib/imad_peak)
+        ex = float(n_loc) * float(plan[1]) * FQ_MUL_PER_MADD / (acc_ms * 1e-3)
+        roof["executed"] = {"fq_mul_per_pair": round(int(plan[1]) * FQ_MUL_PER_MADD, 2), "fq_mul_per_s": ex,
                             "fq_mul_peak_per_s": peak["fq_mul_per_s"], "frac_of_fq_mul_peak": ex / peak["fq_mul_per_s"]}
     if acc_ms:
         pt_bytes = float(n_loc) * float(plan[1]) * 96.0
