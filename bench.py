@@ -72,6 +72,8 @@ def parse_args():
     ap.add_argument("--no-oneshot", action="store_true", help="skip the one-shot seam measurement (N = 1)")
     ap.add_argument("--prove-log-n", type=int, default=0, help="size of the prove sub-record (default 20; 24 at N = 8)")
     ap.add_argument("--prove-steps", type=int, default=5)
+    ap.add_argument("--lib", default=None, help="an A/B build of the library (tools/lab_build.py) instead of lib/libg16cuda.so; "
+                                                "the line then carries \"lab_build\": <path>")
     return ap.parse_args()
 
 
@@ -244,11 +246,18 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+LAB_LIB = None   # --lib
+
+
 def ensure_library(rank, world, dist):
     """Load lib/libg16cuda.so; rebuild it first when it is missing or was built from other sources (the digest of
     csrc/ + include/ is baked into g16_version())."""
     import groth16_cuda
     want = source_hash()
+    if LAB_LIB:   # A/B build: use as is
+        groth16_cuda.DEFAULT_LIB = LAB_LIB
+        lib = groth16_cuda.load_library()
+        return lib, lib.g16_version().decode(), want, False
     if rank == 0:
         stale = not os.path.exists(groth16_cuda.DEFAULT_LIB)
         if not stale:
@@ -359,6 +368,8 @@ def prove_record(args, oracle, devices, log_n, steps, with_setup):
 
 def main():
     args = parse_args()
+    global LAB_LIB
+    LAB_LIB = os.path.abspath(args.lib) if args.lib else None
     if args.impl == "reference":
         return run_reference(args)
 
@@ -647,7 +658,7 @@ def main():
         "gpu_launches": int(launches),
         "stage_ms": {k: float(v) for k, v in zip(["count", "scan", "scatter", "accumulate", "reduce", "combine"], stage_ms)},
         "roofline": roof, "imad_microbench": peak, "cpu_baseline": cpu, "oneshot_seam": oneshot, "prove": prove,
-        "library": {"version": version, "source_hash": src_hash, "matches_source": bool(lib_fresh)},
+        "library": {"version": version, "source_hash": src_hash, "matches_source": bool(lib_fresh), "lab_build": LAB_LIB},
         "clocks": clocks,
     }
     print(json.dumps(line), flush=True)
