@@ -145,6 +145,12 @@ typedef struct g16_pk_host {
 int g16_pk_upload(g16_ctx *ctx, const g16_pk_host *pk, g16_pk **out);
 /* one-time g16_bases_precompute of the five resident arrays (skipped for arrays of < 256 points) */
 int g16_pk_precompute(g16_ctx *ctx, g16_pk *pk);
+/* The same with a promise about the scalars g16_prove will see: the assignment and the H coefficients are below
+ * 2^scalar_bits (0 = full width).  The reference truncates both to 64 bits (crates/groth16-core/src/lib.rs:156-161,
+ * 203-208), so a drop-in for it may pass 64: the tables are then built for a window size that suits 64-bit scalars
+ * (fewer buckets to reduce).  Only a tuning hint: the tables cover all 256 bits, proofs for wider scalars (r, s and
+ * any assignment) stay correct.  Replaces earlier tables of the key. */
+int g16_pk_precompute_bits(g16_ctx *ctx, g16_pk *pk, unsigned scalar_bits);
 void g16_pk_free(g16_pk *pk);
 /* The group part of Prover::prove (crates/groth16-core/src/lib.rs:164-271).
  *   assignment_fr : num_vars x 4 u64, the already truncated `assignment_fr` of lib.rs:156-161

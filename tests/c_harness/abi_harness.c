@@ -22,7 +22,7 @@ static fn_t table[] = {
     F(g16_bases_precompute), F(g16_bases_free), F(g16_bases_len), F(g16_g1_msm), F(g16_g2_msm), F(g16_g1_msm_oneshot),
     F(g16_g2_msm_oneshot), F(g16_g1_msm_device), F(g16_g2_msm_device), F(g16_g1_msm_async), F(g16_g2_msm_async),
     F(g16_g1_combine_partials_device), F(g16_g2_combine_partials_device), F(g16_g1_fixed_base_mul), F(g16_g2_fixed_base_mul),
-    F(g16_g1_fixed_base_mul_device), F(g16_g2_fixed_base_mul_device), F(g16_pk_upload), F(g16_pk_precompute), F(g16_pk_free),
+    F(g16_g1_fixed_base_mul_device), F(g16_g2_fixed_base_mul_device), F(g16_pk_upload), F(g16_pk_precompute), F(g16_pk_precompute_bits), F(g16_pk_free),
     F(g16_prove), F(g16_quotient_h), F(g16_quotient_h_device), F(g16_r1cs_upload), F(g16_r1cs_free), F(g16_r1cs_domain_size), F(g16_r1cs_domain_evals),
     F(g16_r1cs_eval_at), F(g16_setup_crs), F(g16_prove_r1cs), F(g16_g1_serialize), F(g16_g2_serialize), F(g16_g1_deserialize),
     F(g16_g2_deserialize), F(g16_proof_serialize), F(g16_proof_deserialize), F(g16_launch_count), F(g16_ctx_enable_stage_timing),

@@ -142,9 +142,15 @@ def check_prove_in_exponent(ctx, oracle, gens, log_n, seed, precompute, bits_lis
         ctx.pk_precompute(dev_pk)
     r, s = oracle.gen_scalars(seed + 0xaa, 2)
     for bits in bits_list:          # full width, and what the reference's 64-bit truncation produces
+        if precompute and bits == 64:
+            # tables rebuilt for the promised scalar width (g16_pk_precompute_bits); r, s and the (1, r) / (1, s) prefixes
+            # stay full width, and one assignment entry breaks the promise on purpose: a hint, not a contract
+            ctx.pk_precompute(dev_pk, scalar_bits=64)
         w = oracle.gen_scalars(seed + 0x1000 + bits, n, bits)
         w[0] = pm.ONE
         w[7] = 0
+        if precompute and bits == 64 and n > 16:
+            w[11] = oracle.gen_scalars(seed + 0x3000, 1)[0]
         h = oracle.gen_scalars(seed + 0x2000 + bits, n - 1, bits)
         got = ctx.prove(dev_pk, w, h, r, s)
         assert pm.proofs_equal(got, pm.proof_in_exponent(k, 1, w, h, r, s, gens)), f"2^{log_n} proof, {bits}-bit scalars"

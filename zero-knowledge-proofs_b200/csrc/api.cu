@@ -376,16 +376,18 @@ int g16_pk_upload(g16_ctx *ctx, const g16_pk_host *pk, g16_pk **out) {
         *out = h.release();
     });
 }
-int g16_pk_precompute(g16_ctx *ctx, g16_pk *pk) {
+int g16_pk_precompute_bits(g16_ctx *ctx, g16_pk *pk, unsigned scalar_bits) {
     if (!ctx || !pk) return G16_ERR_INVALID;
     return guarded(ctx, [&] {
         require(pk->ctx == &ctx->c, "bad pk handle");
+        require(scalar_bits <= 256, "scalar_bits must be at most 256 (0 = full width)");
         size_t budget = (size_t)24 << 30;
         for (Bases *b : {pk->a.get(), pk->b1.get(), pk->ic.get(), pk->h.get()})
-            if (b->n >= 256) bases_precompute<Fq>(&ctx->c, b, 0, budget);
-        if (pk->b2->n >= 256) bases_precompute<Fq2>(&ctx->c, pk->b2.get(), 0, budget);
+            if (b->n >= 256) bases_precompute<Fq>(&ctx->c, b, 0, budget, scalar_bits);
+        if (pk->b2->n >= 256) bases_precompute<Fq2>(&ctx->c, pk->b2.get(), 0, budget, scalar_bits);
     });
 }
+int g16_pk_precompute(g16_ctx *ctx, g16_pk *pk) { return g16_pk_precompute_bits(ctx, pk, 0); }
 void g16_pk_free(g16_pk *pk) { delete pk; }
 
 

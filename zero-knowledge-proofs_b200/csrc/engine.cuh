@@ -214,16 +214,26 @@ inline MsmPlan make_shared_plan(unsigned c, size_t stride) {
     return p;
 }
 
-// window size for a precomputed table over n bases: every digit costs one mixed addition, the single
-// shared bucket set costs two full additions per bucket; the table must fit `budget` bytes and 31 bits.
-inline unsigned choose_precompute_c(size_t n, size_t point_bytes, size_t budget) {
+// window size for a precomputed table over n bases: every non-zero digit costs one mixed addition, the single shared
+// bucket set two full additions per bucket (charged as three mixed additions: the reduction runs below the accumulation's
+// efficiency), and the table (always ceil(256 / c) windows: any scalar stays valid) must fit `budget` bytes and 31 bits.
+// Checked against sweeps on B200: 2^20 bases full width G2 c = 18 / 19 / 20: 22.2 / 20.8 / 19.6 ms; 64-bit scalars c = 16 /
+// 17 / 18 / 20: G1 4.63 / 2.59 / 2.93 / 3.45 ms, G2 13.8 / 7.6 / 8.3 / 10.8 ms (profiles/r02_run27_lab_window_choice.txt).
+// scalar_bits < 255: the caller knows its scalars are that short (the reference truncates the witness and the H
+// coefficients to 64 bits, crates/groth16-core/src/lib.rs:156-161,203-208), so only ceil((bits + 1) / c) windows hold
+// non-zero digits (the + 1: the carry of the signed recoding -- c = 16 puts half of all 64-bit scalars into a fifth
+// window) and a smaller c -- fewer buckets to reduce -- wins.
+inline unsigned choose_precompute_c(size_t n, size_t point_bytes, size_t budget, unsigned scalar_bits = 255) {
     unsigned best_c = 0;
     double best = 1e300;
+    const double bucket_cost = 30.0;
+    const unsigned bits = scalar_bits == 0 || scalar_bits > 255 ? 255 : scalar_bits;
     for (unsigned c = 8; c <= 24; ++c) {
         double nwin = (256 + c - 1) / c;
         if (nwin * (double)n * point_bytes > (double)budget) continue;
         if (nwin * (double)n >= 2147483648.0) continue;
-        double cost = nwin * (double)n * 10.0 + (double)(1ull << (c - 1)) * 30.0;
+        double used = std::min(nwin, (double)((bits + 1 + c - 1) / c));
+        double cost = used * (double)n * 10.0 + (double)(1ull << (c - 1)) * bucket_cost;
         if (cost < best) { best = cost; best_c = c; }
     }
     return best_c;
@@ -499,7 +509,7 @@ std::unique_ptr<Bases> bases_upload(Context *ctx, const uint64_t *xy, const uint
 // Build the table of multiples for every shard (one-time, at upload).  c = 0: choose from the shard size
 // and `budget_bytes` of device memory per shard.  Returns the window size used (0 = not applicable).
 template <class F>
-unsigned bases_precompute(Context *ctx, Bases *bases, unsigned c, size_t budget_bytes) {
+unsigned bases_precompute(Context *ctx, Bases *bases, unsigned c, size_t budget_bytes, unsigned scalar_bits = 255) {
     unsigned used = 0;
     struct Pending { BasesShard *sh; uint32_t *table; unsigned cc; };
     std::vector<Pending> pending;
@@ -513,7 +523,7 @@ unsigned bases_precompute(Context *ctx, Bases *bases, unsigned c, size_t budget_
             Device &dv = ctx->devs[sh.dev];
             set_device(dv.id);
             size_t point_bytes = 2 * FieldWords<F>::N * 4;
-            unsigned cc = c ? c : choose_precompute_c(sh.n, point_bytes, budget_bytes);
+            unsigned cc = c ? c : choose_precompute_c(sh.n, point_bytes, budget_bytes, scalar_bits);
             if (!c && cc == 0) continue;   // nothing fits the budget: this shard stays plain
             if (cc < 8 || cc > 24) throw Error{G16_ERR_INVALID, "precompute window bits must be in [8, 24]"};
             uint32_t nwin = (256 + cc - 1) / cc;

@@ -40,7 +40,7 @@ EXPORTS = [
     "g16_g1_combine_partials_device", "g16_g2_combine_partials_device",
     "g16_g1_fixed_base_mul", "g16_g2_fixed_base_mul",
     "g16_g1_fixed_base_mul_device", "g16_g2_fixed_base_mul_device",
-    "g16_pk_upload", "g16_pk_free", "g16_prove", "g16_pk_precompute", "g16_quotient_h", "g16_quotient_h_device",
+    "g16_pk_upload", "g16_pk_free", "g16_prove", "g16_pk_precompute", "g16_pk_precompute_bits", "g16_quotient_h", "g16_quotient_h_device",
     "g16_r1cs_upload", "g16_r1cs_free", "g16_r1cs_domain_size", "g16_r1cs_domain_evals", "g16_r1cs_eval_at",
     "g16_setup_crs", "g16_prove_r1cs",
     "g16_g1_serialize", "g16_g2_serialize", "g16_g1_deserialize", "g16_g2_deserialize",
@@ -120,6 +120,7 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.g16_bases_len.restype = sz
     lib.g16_pk_upload.argtypes = [vp, ctypes.POINTER(_PkHost), ctypes.POINTER(vp)]
     lib.g16_pk_precompute.argtypes = [vp, vp]
+    lib.g16_pk_precompute_bits.argtypes = [vp, vp, ctypes.c_uint]
     lib.g16_pk_free.argtypes = [vp]
     lib.g16_pk_free.restype = None
     lib.g16_prove.argtypes = [vp, vp, vp, sz, vp, sz, vp, vp, vp, vp, vp, vp, vp, vp]
@@ -429,9 +430,11 @@ class Context:
         self._check(self.lib.g16_pk_upload(self.handle, ctypes.byref(s), ctypes.byref(h)))
         return ProvingKeyDevice(self, h.value)
 
-    def pk_precompute(self, pk: ProvingKeyDevice):
-        """One-time tables of multiples for the five resident arrays (g16_pk_precompute)."""
-        self._check(self.lib.g16_pk_precompute(self.handle, pk.handle))
+    def pk_precompute(self, pk: ProvingKeyDevice, scalar_bits: int = 0):
+        """One-time tables of multiples for the five resident arrays (g16_pk_precompute / g16_pk_precompute_bits).
+        scalar_bits: the assignment and H coefficients are promised to be below 2^scalar_bits (0 = full width; 64 is
+        what the reference's truncation yields) -- a tuning hint only, any scalar stays valid."""
+        self._check(self.lib.g16_pk_precompute_bits(self.handle, pk.handle, scalar_bits))
 
     def prove(self, pk: ProvingKeyDevice, assignment_fr, h_coeffs, r, s):
         """Group part of Prover::prove.  Returns ((a_xy, a_inf), (b_xy, b_inf), (c_xy, c_inf))."""

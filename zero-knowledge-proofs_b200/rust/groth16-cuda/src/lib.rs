@@ -276,6 +276,12 @@ impl<'a> DeviceProvingKey<'a> {
     }
     /// One-time tables of multiples for the five resident arrays (`g16_pk_precompute`).
     pub fn precompute(&mut self) -> Result<(), String> { check(self.ctx.raw, unsafe { g16_pk_precompute(self.ctx.raw, self.raw) }) }
+    /// The same for scalars promised to be below `2^scalar_bits` (`g16_pk_precompute_bits`): `Prover::prove` truncates the
+    /// assignment and the H coefficients to 64 bits (`crates/groth16-core/src/lib.rs:156-161,203-208`), so the drop-in
+    /// passes 64.  A tuning hint only: wider scalars (r, s) stay correct.
+    pub fn precompute_for_bits(&mut self, scalar_bits: u32) -> Result<(), String> {
+        check(self.ctx.raw, unsafe { g16_pk_precompute_bits(self.ctx.raw, self.raw, scalar_bits as c_uint) })
+    }
     /// The group part of `Prover::prove` (`lib.rs:164-271`): `assignment_fr` = the truncated assignment of `:156-161`,
     /// `h_coeffs` = the truncated quotient coefficients of `:203-208`, `r`, `s` of `:152-153`.
     pub fn prove(&self, assignment_fr: &[Fr], h_coeffs: &[Fr], r: &Fr, s: &Fr) -> Result<ProofPoints, String> {

@@ -82,6 +82,7 @@ extern "C" {
     // ---- prove schedule
     pub fn g16_pk_upload(ctx: *mut g16_ctx, pk: *const g16_pk_host, out: *mut *mut g16_pk) -> c_int;
     pub fn g16_pk_precompute(ctx: *mut g16_ctx, pk: *mut g16_pk) -> c_int;
+    pub fn g16_pk_precompute_bits(ctx: *mut g16_ctx, pk: *mut g16_pk, scalar_bits: c_uint) -> c_int;
     pub fn g16_pk_free(pk: *mut g16_pk);
     pub fn g16_prove(ctx: *mut g16_ctx, pk: *const g16_pk, assignment_fr: *const u64, num_vars: usize, h_coeffs: *const u64, num_h: usize,
                      r: *const u64, s: *const u64, a_xy: *mut u64, a_inf: *mut u8, b_xy: *mut u64, b_inf: *mut u8, c_xy: *mut u64, c_inf: *mut u8) -> c_int;

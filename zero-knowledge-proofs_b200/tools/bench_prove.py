@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-precompute", action="store_true")
+    ap.add_argument("--no-precompute-bits", action="store_true", help="keep the full-width tables for the 64-bit scalars")
     ap.add_argument("--timeline", action="store_true", help="print the per-lane stage timeline of one prove")
     ap.add_argument("--lib", default=None, help="alternative build of the library (A/B experiments, tools/lab_build.py)")
     args = ap.parse_args()
@@ -72,7 +73,9 @@ def main():
     s = oracle.gen_scalars(0xbb, 1)[0]
     one = np.array(bls.fr_to_mont(1), dtype=np.uint64)
 
-    for dist, bits in (("ref_faithful_u64", 64), ("full_width", 255)):
+    for dist, bits in (("full_width", 255), ("ref_faithful_u64", 64)):
+        if bits == 64 and not args.no_precompute_bits and not args.no_precompute:
+            ctx.pk_precompute(dev_pk, scalar_bits=64)   # tables for the scalars the reference's truncation yields
         w = oracle.gen_scalars(0x1000 + bits, n, bits)
         w[0] = one                                    # assignment[0] is the constant 1
         h = oracle.gen_scalars(0x2000 + bits, n - 1, bits)
