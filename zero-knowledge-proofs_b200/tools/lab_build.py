@@ -28,6 +28,11 @@ VARIANTS = {
     # name: {unit: [flags]}   (shipped: accumulate 64 threads x 6 blocks (G1); item floor 16; reduction split 15 / 15)
     "g1_b128": {"k_acc_g1.cu": ["-DG16_ACC_BLOCK=128", "-DG16_ACC_MIN_BLOCKS_G1=3"]},
     "g1_b32_mb12": {"k_acc_g1.cu": ["-DG16_ACC_BLOCK=32", "-DG16_ACC_MIN_BLOCKS_G1=12"]},
+    "g1_mb5": {"k_acc_g1.cu": ["-DG16_ACC_MIN_BLOCKS_G1=5"]},
+    "g1_mb7": {"k_acc_g1.cu": ["-DG16_ACC_MIN_BLOCKS_G1=7"]},
+    "g1_b128_mb3": {"k_acc_g1.cu": ["-DG16_ACC_BLOCK=128", "-DG16_ACC_MIN_BLOCKS_G1=3"]},
+    "g2_mb2_b128": {"k_acc_g2.cu": ["-DG16_ACC_BLOCK=128", "-DG16_ACC_MIN_BLOCKS_G2=2"]},
+    "g2_b32": {"k_acc_g2.cu": ["-DG16_ACC_BLOCK=32", "-DG16_ACC_MIN_BLOCKS_G2=8"]},
     "g2_b128": {"k_acc_g2.cu": ["-DG16_ACC_BLOCK=128"]},
     "g2_acc_fq2_calls": {"k_acc_g2.cu": ["-DG16_COLD_FQ2=1"]},
     "g2_acc_fq2_calls_mb6": {"k_acc_g2.cu": ["-DG16_COLD_FQ2=1", "-DG16_ACC_MIN_BLOCKS_G2=6"]},
