@@ -87,3 +87,10 @@ def test_emu_prove_multi_device_schedule(emu_ctx, oracle, gens):
             prove_cases.check_random_key(ctx, emu_ctx, oracle, gens, n=23, seed=len(devs))
         finally:
             ctx.close()
+
+
+def test_emu_prove_with_scalar_width_hint(emu_ctx, oracle, gens):
+    """g16_pk_precompute_bits: tables chosen for 64-bit scalars (what the reference's truncation yields), proofs checked in
+    the exponent -- including one full-width assignment entry and the full-width r, s that break the promise on purpose."""
+    import prove_cases
+    prove_cases.check_prove_in_exponent(emu_ctx, oracle, gens, log_n=9, seed=0x51, precompute=True, bits_list=(64, 255))
