@@ -64,6 +64,10 @@ int g16_ctx_set_window_bits(g16_ctx *ctx, unsigned c);
  * the same bucket array as soon as it has arrived, so only the first small copy is exposed.  0 restores the default
  * (2^19).  Results are unchanged. */
 int g16_ctx_set_h2d_pipeline_min(g16_ctx *ctx, size_t min_scalars);
+/* tuning: the longest run of additions one thread walks serially in the bucket accumulation (buckets with more entries
+ * are cut into slices whose sums are folded afterwards).  0 restores the default: chosen per call from its size (16 for
+ * small calls, up to 256 for large ones).  Range [4, 256].  Results are unchanged. */
+int g16_ctx_set_item_max(g16_ctx *ctx, unsigned item_max);
 int g16_device_count(void);
 const char *g16_version(void);
 

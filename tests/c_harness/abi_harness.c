@@ -17,7 +17,7 @@ typedef void (*fn_t)(void);
 #define F(x) (fn_t)(x)
 static fn_t table[] = {
     F(g16_ctx_create), F(g16_ctx_destroy), F(g16_last_error), F(g16_ctx_set_stream), F(g16_ctx_synchronize),
-    F(g16_ctx_set_window_bits), F(g16_ctx_set_h2d_pipeline_min), F(g16_device_count), F(g16_version),
+    F(g16_ctx_set_window_bits), F(g16_ctx_set_h2d_pipeline_min), F(g16_ctx_set_item_max), F(g16_device_count), F(g16_version),
     F(g16_g1_bases_upload), F(g16_g2_bases_upload), F(g16_g1_bases_from_device), F(g16_g2_bases_from_device),
     F(g16_bases_precompute), F(g16_bases_free), F(g16_bases_len), F(g16_g1_msm), F(g16_g2_msm), F(g16_g1_msm_oneshot),
     F(g16_g2_msm_oneshot), F(g16_g1_msm_device), F(g16_g2_msm_device), F(g16_g1_msm_async), F(g16_g2_msm_async),

@@ -671,6 +671,16 @@ int g16_quotient_h_device(g16_ctx *ctx, void *dev_abc, size_t n, void *dev_h, vo
 // ---- test hooks --------------------------------------------------------------------------------
 unsigned long long g16_launch_count(void) { return launch_count(); }
 
+int g16_ctx_set_item_max(g16_ctx *ctx, unsigned item_max) {
+    if (!ctx) return G16_ERR_INVALID;
+    return guarded(ctx, [&] {
+        require(item_max == 0 || (item_max >= 4 && item_max <= k_item_max()), "item_max must be 0 or in [4, 256]");
+        for (auto &d : ctx->c.devs) {
+            d.item_max_override = item_max;
+            for (auto &l : d.extra) l->item_max_override = item_max;
+        }
+    });
+}
 int g16_ctx_enable_stage_timing(g16_ctx *ctx, int on) {
     if (!ctx) return G16_ERR_INVALID;
     for (auto &d : ctx->c.devs) {

@@ -86,6 +86,7 @@ struct Device {
     Workspace ws;
     StageTimer timer;
     MsmPlan last_plan{};
+    uint32_t item_max_override = 0;   // g16_ctx_set_item_max: 0 = chosen per call from its size
     // extra lanes (own stream + workspace) on the same GPU: lets the latency-bound tail of one MSM
     // (reduction tree, inversion) overlap the bucket accumulation of another (prove schedule)
     std::vector<std::unique_ptr<Device>> extra;
@@ -278,6 +279,7 @@ struct MsmJob {
     uint32_t *split_list = nullptr, *entries = nullptr, *staging = nullptr, *part_cursor = nullptr, *buckets = nullptr, *chunk_out = nullptr;
     WorkItem *items = nullptr;
     uint32_t item_max = 0;      // of the range `front` handled last
+    size_t item_min_ = 1;       // shortest item limit the workspaces were sized for
     size_t n_entries = 0;
 
     // bases [first_, first_ + n_) of the shard; ranges of at most n_max_ scalars will be fed (0 = the whole call at once).
@@ -300,7 +302,8 @@ struct MsmJob {
         scan_tmp = ws.scan_tmp.as<uint32_t>(k_scan_tmp_words(total + 1));
         bins = ws.bins.as<uint32_t>(2 * (nbins + 1));
         bin_cursor = bins + nbins + 1;
-        const size_t item_min = std::min<size_t>(k_item_max(), ITEM_FLOOR);
+        const size_t item_min = std::min<size_t>(k_item_max(), dv.item_max_override ? std::min<size_t>(ITEM_FLOOR, dv.item_max_override) : ITEM_FLOOR);
+        item_min_ = item_min;
         const size_t max_split_buckets = max_entries / item_min + 1;     // buckets longer than the shortest item limit
         const size_t max_split = 2 * max_split_buckets + 16;             // chunks they are cut into
         items = (WorkItem *)ws.items.need((total + max_split) * k_item_bytes());
@@ -332,6 +335,7 @@ struct MsmJob {
         k_exclusive_scan(s, counts, counts, total + 1, scan_tmp);
         uint32_t *offsets = counts;
         item_max = (uint32_t)std::min<size_t>(k_item_max(), std::max<size_t>(ITEM_FLOOR, n_entries >> ITEM_SHIFT));
+        if (dv.item_max_override) item_max = std::min<uint32_t>(k_item_max(), std::max<uint32_t>(dv.item_max_override, (uint32_t)item_min_));
         dev_memset(bins, 0, (nbins + 1) * sizeof(uint32_t), s);
         k_item_count(s, total, offsets, item_max, bins);
         k_exclusive_scan(s, bins, bins, nbins + 1, scan_tmp);

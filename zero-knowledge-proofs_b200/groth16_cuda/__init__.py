@@ -32,7 +32,7 @@ G1_AFFINE_WORDS, G2_AFFINE_WORDS = 25, 49
 
 EXPORTS = [
     "g16_version", "g16_device_count", "g16_ctx_create", "g16_ctx_destroy", "g16_last_error",
-    "g16_ctx_set_stream", "g16_ctx_synchronize", "g16_ctx_set_window_bits", "g16_ctx_set_h2d_pipeline_min",
+    "g16_ctx_set_stream", "g16_ctx_synchronize", "g16_ctx_set_window_bits", "g16_ctx_set_h2d_pipeline_min", "g16_ctx_set_item_max",
     "g16_g1_bases_upload", "g16_g2_bases_upload", "g16_g1_bases_from_device", "g16_g2_bases_from_device",
     "g16_bases_free", "g16_bases_len", "g16_bases_precompute",
     "g16_g1_msm", "g16_g2_msm", "g16_g1_msm_oneshot", "g16_g2_msm_oneshot",
@@ -103,6 +103,7 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.g16_ctx_synchronize.argtypes = [vp]
     lib.g16_ctx_set_window_bits.argtypes = [vp, ctypes.c_uint]
     lib.g16_ctx_set_h2d_pipeline_min.argtypes = [vp, sz]
+    lib.g16_ctx_set_item_max.argtypes = [vp, ctypes.c_uint]
     for g in ("g1", "g2"):
         getattr(lib, f"g16_{g}_bases_upload").argtypes = [vp, vp, vp, sz, ctypes.POINTER(vp)]
         getattr(lib, f"g16_{g}_bases_from_device").argtypes = [vp, vp, sz, ctypes.POINTER(vp)]
@@ -272,6 +273,10 @@ class Context:
     def set_h2d_pipeline_min(self, min_scalars: int):
         """Host-scalar MSMs of at least this many scalars per device pipeline their H2D copy (0 = default 2^19)."""
         self._check(self.lib.g16_ctx_set_h2d_pipeline_min(self.handle, min_scalars))
+
+    def set_item_max(self, item_max: int):
+        """Tuning: longest serial run of additions per thread in the bucket accumulation (0 = chosen per call)."""
+        self._check(self.lib.g16_ctx_set_item_max(self.handle, item_max))
 
     # ---- bases
     def _upload(self, g: str, xy, inf) -> Bases:

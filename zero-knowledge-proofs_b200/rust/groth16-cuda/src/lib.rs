@@ -57,6 +57,8 @@ impl Context {
     pub fn set_window_bits(&self, c: u32) -> Result<(), String> { check(self.raw, unsafe { g16_ctx_set_window_bits(self.raw, c as c_uint) }) }
     /// Host-scalar MSMs of at least this many scalars per device pipeline their H2D copy; 0 = default (2^19).
     pub fn set_h2d_pipeline_min(&self, min_scalars: usize) -> Result<(), String> { check(self.raw, unsafe { g16_ctx_set_h2d_pipeline_min(self.raw, min_scalars) }) }
+    /// Tuning: longest serial run of additions per thread in the bucket accumulation (0 = chosen per call).
+    pub fn set_item_max(&self, item_max: u32) -> Result<(), String> { check(self.raw, unsafe { g16_ctx_set_item_max(self.raw, item_max as c_uint) }) }
     /// Kernels launched by the library since it was loaded (bench / tests).
     pub fn launch_count() -> u64 { unsafe { g16_launch_count() as u64 } }
     /// CUDA-event timing of the stages of the next MSMs on a single-device context (bench / tests).

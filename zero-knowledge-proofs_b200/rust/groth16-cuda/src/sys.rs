@@ -54,6 +54,7 @@ extern "C" {
     pub fn g16_ctx_synchronize(ctx: *mut g16_ctx) -> c_int;
     pub fn g16_ctx_set_window_bits(ctx: *mut g16_ctx, c: c_uint) -> c_int;
     pub fn g16_ctx_set_h2d_pipeline_min(ctx: *mut g16_ctx, min_scalars: usize) -> c_int;
+    pub fn g16_ctx_set_item_max(ctx: *mut g16_ctx, item_max: c_uint) -> c_int;
     pub fn g16_device_count() -> c_int;
     pub fn g16_version() -> *const c_char;
     // ---- variable-base MSM
