@@ -243,11 +243,13 @@ inline unsigned choose_precompute_c(size_t n, size_t point_bytes, size_t budget,
 constexpr size_t SCATTER_TWO_PASS_BYTES = (size_t)96 << 20;   // `entries` larger than this (~L2) are scattered in two passes
 constexpr uint32_t REDUCE_LOG_L = 5;
 // longest work item: 256 additions when the call is large (a serial walk of 256 is noise), shorter when it is small
-// and the longest item would set the kernel's duration: max(ITEM_FLOOR, entries >> ITEM_SHIFT).  Floor 16: at
-// 2^16 / 2^18 pairs the 2^15 buckets alone are too few threads, cutting them into slices of <= 16 / 32 entries takes
-// the accumulation from 0.79 to 0.70 ms and from 2.39 to 2.02 ms (profiles/README.md run 23)
+// and the longest item would set the kernel's duration: max(ITEM_FLOOR, entries >> ITEM_SHIFT).  The floor only acts
+// below ~2^17 pairs: at 2^16 pairs the 2^15 buckets (32 entries each) alone are too few threads, and slices of <= 11
+// entries -- three per bucket, 1.7 waves of work items -- beat slices of 16 (accumulate 0.65 -> 0.60 ms for G1, 2.07 ->
+// 1.68 ms for G2; sweep over 6 .. 128 in profiles/r02_run30_sweep_item_max.jsonl, results bit-identical throughout).
+// g16_ctx_set_item_max overrides the choice per context.
 #ifndef G16_ITEM_FLOOR
-#define G16_ITEM_FLOOR 16
+#define G16_ITEM_FLOOR 11
 #endif
 constexpr size_t ITEM_FLOOR = G16_ITEM_FLOOR;   // (tools/lab_build.py overrides the G16_* constants for A/B builds)
 constexpr unsigned ITEM_SHIFT = 17;
