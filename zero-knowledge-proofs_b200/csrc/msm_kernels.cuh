@@ -495,6 +495,9 @@ struct ChunkMergeSerial {
 //   Y'[g] = sum_j Y[gL + j] + 2^shift * sum_j j * X[gL + j]
 // With shift = log2(L) * level this telescopes to  sum_i i * X0[i] = Y_final[0]
 // (derivation in DESIGN.md "Bucket reduction").
+#ifndef G16_RED_TWO_LOOPS_G2
+#define G16_RED_TWO_LOOPS_G2 1   // see ReduceLevel::run; 0 builds the one-loop form for A/B runs
+#endif
 #ifndef G16_RED_MIN_BLOCKS_G2
 #define G16_RED_MIN_BLOCKS_G2 1   // left to ptxas (255 registers); A/B builds: tools/lab_build.py
 #endif
@@ -502,6 +505,7 @@ template <class F>
 struct ReduceLevel {
     static constexpr int BLOCK = 64;
     static constexpr int MIN_BLOCKS = F::N == 12 ? 1 : G16_RED_MIN_BLOCKS_G2;
+    static constexpr bool TWO_LOOPS = F::N == 24 && G16_RED_TWO_LOOPS_G2;
     G16_HD static void run(size_t t, const uint32_t *X, const uint32_t *Y, uint32_t n_in, uint32_t n_out, uint32_t L,
                            uint32_t shift, uint32_t *Xo, uint32_t *Yo) {
         uint32_t w = (uint32_t)(t / n_out), g = (uint32_t)(t % n_out);
@@ -509,14 +513,36 @@ struct ReduceLevel {
         uint32_t lo = g * L;
         uint32_t hi = lo + L < n_in ? lo + L : n_in;
         XYZZ<F> running = XYZZ<F>::inf(), acc = XYZZ<F>::inf();
-        for (uint32_t i = hi; i-- > lo + 1;) {
-            XYZZ<F> x = load_xyzz<F>(X, base + i);
-            xyzz_add(running, x);
-            xyzz_add(acc, running);
-        }
-        {
-            XYZZ<F> x0 = load_xyzz<F>(X, base + lo);
-            xyzz_add(running, x0);
+        if (TWO_LOOPS) {
+            // G2: three projective points alive at once (x, running, acc = 288 words) is what makes this level spill;
+            // so first the suffix sums alone, parked IN PLACE of the entries they replace (the input of a level is
+            // dead after it: bucket array or a workspace buffer of the previous level), then their plain sum.  Same
+            // additions in the same order; 768 bytes of extra traffic per entry.
+            uint32_t *Xm = const_cast<uint32_t *>(X);
+            for (uint32_t i = hi; i-- > lo + 1;) {
+                XYZZ<F> x = load_xyzz<F>(X, base + i);
+                xyzz_add(running, x);
+                store_xyzz<F>(Xm, base + i, running);
+            }
+            {
+                XYZZ<F> x0 = load_xyzz<F>(X, base + lo);
+                xyzz_add(running, x0);
+            }
+            store_xyzz<F>(Xo, (size_t)w * n_out + g, running);
+            for (uint32_t i = hi; i-- > lo + 1;) {
+                XYZZ<F> sfx = load_xyzz<F>(X, base + i);
+                xyzz_add(acc, sfx);
+            }
+        } else {
+            for (uint32_t i = hi; i-- > lo + 1;) {
+                XYZZ<F> x = load_xyzz<F>(X, base + i);
+                xyzz_add(running, x);
+                xyzz_add(acc, running);
+            }
+            {
+                XYZZ<F> x0 = load_xyzz<F>(X, base + lo);
+                xyzz_add(running, x0);
+            }
         }
         for (uint32_t s = 0; s < shift; ++s) xyzz_dbl(acc);
         if (Y) {
@@ -525,7 +551,7 @@ struct ReduceLevel {
                 xyzz_add(acc, y);
             }
         }
-        store_xyzz<F>(Xo, (size_t)w * n_out + g, running);
+        if (!TWO_LOOPS) store_xyzz<F>(Xo, (size_t)w * n_out + g, running);
         store_xyzz<F>(Yo, (size_t)w * n_out + g, acc);
     }
 };
