@@ -498,14 +498,20 @@ struct ChunkMergeSerial {
 #ifndef G16_RED_TWO_LOOPS_G2
 #define G16_RED_TWO_LOOPS_G2 1   // see ReduceLevel::run; 0 builds the one-loop form for A/B runs
 #endif
+#ifndef G16_RED_TWO_LOOPS_G1
+#define G16_RED_TWO_LOOPS_G1 0   // G1 keeps one loop: 0.97 ms against 1.00 (two loops, 216 registers) / 1.06 (two loops at 168
+#endif                           // registers, 6 blocks per SM) at 2^19 buckets, 2.96 against 3.24 ms at 2^21 (profiles/r02_run34_*)
+#ifndef G16_RED_MIN_BLOCKS_G1
+#define G16_RED_MIN_BLOCKS_G1 1
+#endif
 #ifndef G16_RED_MIN_BLOCKS_G2
 #define G16_RED_MIN_BLOCKS_G2 1   // left to ptxas (255 registers); A/B builds: tools/lab_build.py
 #endif
 template <class F>
 struct ReduceLevel {
     static constexpr int BLOCK = 64;
-    static constexpr int MIN_BLOCKS = F::N == 12 ? 1 : G16_RED_MIN_BLOCKS_G2;
-    static constexpr bool TWO_LOOPS = F::N == 24 && G16_RED_TWO_LOOPS_G2;
+    static constexpr int MIN_BLOCKS = F::N == 12 ? G16_RED_MIN_BLOCKS_G1 : G16_RED_MIN_BLOCKS_G2;
+    static constexpr bool TWO_LOOPS = F::N == 24 ? G16_RED_TWO_LOOPS_G2 : G16_RED_TWO_LOOPS_G1;
     G16_HD static void run(size_t t, const uint32_t *X, const uint32_t *Y, uint32_t n_in, uint32_t n_out, uint32_t L,
                            uint32_t shift, uint32_t *Xo, uint32_t *Yo) {
         uint32_t w = (uint32_t)(t / n_out), g = (uint32_t)(t % n_out);

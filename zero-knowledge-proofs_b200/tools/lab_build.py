@@ -44,6 +44,9 @@ VARIANTS = {
     "g2_pair_mb4": {"k_acc_g2.cu": ["-DG16_G2_ACC_THREAD=0", "-DG16_PAIR_MIN_BLOCKS=4"]},
     "g2_acc_karatsuba": {"k_acc_g2.cu": ["-DG16_FQ2_DUAL=0"]},
     "g2_red_dual": {"k_red_g2.cu": ["-UG16_FQ2_DUAL", "-DG16_FQ2_DUAL=1"]},
+    "g1_red_two_loops": {"k_red_g1.cu": ["-DG16_RED_TWO_LOOPS_G1=1"]},
+    "g1_red_two_loops_mb6": {"k_red_g1.cu": ["-DG16_RED_TWO_LOOPS_G1=1", "-DG16_RED_MIN_BLOCKS_G1=6"]},
+    "g1_red_mb6": {"k_red_g1.cu": ["-DG16_RED_MIN_BLOCKS_G1=6"]},
     "g2_red_one_loop": {"k_red_g2.cu": ["-DG16_RED_TWO_LOOPS_G2=0"]},
     "g2_red_mb5": {"k_red_g2.cu": ["-DG16_RED_MIN_BLOCKS_G2=5"]},
     "g2_red_mb6": {"k_red_g2.cu": ["-DG16_RED_MIN_BLOCKS_G2=6"]},
