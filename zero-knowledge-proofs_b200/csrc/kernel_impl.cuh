@@ -51,7 +51,7 @@ void k_tile_reduce(stream_t s, uint32_t windows, const uint32_t *X, const uint32
                    uint32_t n_out, uint32_t T, uint32_t shift, uint32_t *Xo, uint32_t *Y1o, uint32_t *Y2o) {
 #ifndef G16_EMU
     // T = entries per tile; elements (quads of lanes) = T / TILE_K, at least one warp of 8
-    uint32_t elems = T / TILE_K < 8 ? 8 : T / TILE_K;
+    uint32_t elems = T / TileShape<F>::K < 8 ? 8 : T / TileShape<F>::K;
     size_t smem = (size_t)elems * (4 * F::N + 1) * sizeof(uint32_t);
     tile_reduce_kernel<F><<<dim3(n_out, windows, (Y1 || Y2) ? 2 : 1), 4 * elems, smem, s>>>(X, Y1, Y2, n_in, n_out, T, shift, Xo, Y1o, Y2o);
     G16_CUDA_CHECK(cudaGetLastError());

@@ -579,6 +579,21 @@ struct ReduceLevel {
 // stride (conflict free for the quad-broadcast reads).
 constexpr int TILE_K = 4;        // consecutive entries folded serially by each element before the block scan
 constexpr int TILE_ELEMS = 64;   // elements (quads) per block -> 256 threads, TILE_K * TILE_ELEMS entries per tile
+// Per group: the same 256 entries per tile as K entries x 256 / K elements.  G2 runs 8 x 32: blocks of 128 threads may
+// use 254 registers (two per SM) where 256 threads were held to 128, and a tile needs a third fewer cooperative
+// additions (fold 15 x 32 + scan / tree 10 x 32 against 7 x 64 + 12 x 64): bucket reduction 4.53 -> 4.28 ms at 2^19 buckets
+// (profiles/r02_run36_lab_g2_tile_k8.txt).  (G16_TILE_K_G1 / _G2: A/B builds, tools/lab_build.py)
+#ifndef G16_TILE_K_G2
+#define G16_TILE_K_G2 8
+#endif
+#ifndef G16_TILE_K_G1
+#define G16_TILE_K_G1 4
+#endif
+template <class F>
+struct TileShape {
+    static constexpr int K = F::N == 24 ? G16_TILE_K_G2 : G16_TILE_K_G1;
+    static constexpr int ELEMS = TILE_K * TILE_ELEMS / K;
+};
 #if !defined(G16_EMU) && defined(__CUDACC__)
 template <class F>
 __device__ __forceinline__ void tile_put(uint32_t *sm, int e, int q, const XYZZ<F> &p) {
@@ -600,10 +615,11 @@ __device__ __forceinline__ XYZZ<F> tile_get(const uint32_t *sm, int e) {
     return p;
 }
 template <class F>
-__global__ void __launch_bounds__(4 * TILE_ELEMS, 2) tile_reduce_kernel(const uint32_t *X, const uint32_t *Y1, const uint32_t *Y2,
+__global__ void __launch_bounds__(4 * TileShape<F>::ELEMS, 2) tile_reduce_kernel(const uint32_t *X, const uint32_t *Y1, const uint32_t *Y2,
                                                                      uint32_t n_in, uint32_t n_out, uint32_t tile_entries,
                                                                      uint32_t shift, uint32_t *Xo, uint32_t *Y1o, uint32_t *Y2o) {
     extern __shared__ uint32_t sm[];
+    constexpr int TILE_K = TileShape<F>::K;   // (shadows the global default)
     const int T = blockDim.x >> 2;                 // elements in this block; T * TILE_K >= tile_entries
     const int e = threadIdx.x >> 2, q = threadIdx.x & 3;
     const int warp_e0 = (threadIdx.x & ~31) >> 2;  // first element of this warp (8 elements per warp)

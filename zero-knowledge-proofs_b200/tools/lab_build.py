@@ -47,6 +47,9 @@ VARIANTS = {
     "g1_red_two_loops": {"k_red_g1.cu": ["-DG16_RED_TWO_LOOPS_G1=1"]},
     "g1_red_two_loops_mb6": {"k_red_g1.cu": ["-DG16_RED_TWO_LOOPS_G1=1", "-DG16_RED_MIN_BLOCKS_G1=6"]},
     "g1_red_mb6": {"k_red_g1.cu": ["-DG16_RED_MIN_BLOCKS_G1=6"]},
+    "g2_tile_k4": {"k_red_g2.cu": ["-DG16_TILE_K_G2=4"]},
+    "g2_tile_k16": {"k_red_g2.cu": ["-DG16_TILE_K_G2=16"]},
+    "g1_tile_k8": {"k_red_g1.cu": ["-DG16_TILE_K_G1=8"]},
     "g2_red_one_loop": {"k_red_g2.cu": ["-DG16_RED_TWO_LOOPS_G2=0"]},
     "g2_red_mb5": {"k_red_g2.cu": ["-DG16_RED_MIN_BLOCKS_G2=5"]},
     "g2_red_mb6": {"k_red_g2.cu": ["-DG16_RED_MIN_BLOCKS_G2=6"]},
