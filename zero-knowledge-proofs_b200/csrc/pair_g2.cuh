@@ -1,4 +1,8 @@
-// G2 bucket accumulation on lane pairs (device only).
+// G2 bucket accumulation on lane pairs (device only).  NOT the shipped path: built only with -DG16_G2_ACC_THREAD=0
+// (tools/lab_build.py g2_pair).  Bit-exact on B200 (all G2 parity tests), measured 16.9 ms at 168 registers / 15.8 ms at 255
+// for the 2^20 accumulation against 14.1 ms for the one-thread kernel once that uses the same two-product multiplication
+// (profiles/r02_run20_lab_g2_pair_and_dual.txt): kept because its arithmetic is the starting point for a
+// lane-pair form of the G2 bucket REDUCTION.
 //
 // The one-thread form of the G2 mixed addition (ec.cuh with F = Fq2) needs more than the 255 registers a thread can
 // have: it spills, runs two warps per scheduler and reaches 74 % of the Fq-multiply peak where the G1 kernel reaches
